@@ -1,0 +1,287 @@
+"""ctypes binding of the C ABI in include/viennaray_b200.h (the same calls a
+cgo / JNI / C++ host would make).  Loading fails loudly when the CUDA library
+has not been built; there is no fallback of any kind."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libviennaray_b200.so")
+
+_vp = C.c_void_p
+FLUX_FIXED_SCALE = float(2**30)
+
+PARTICLE_DIFFUSE, PARTICLE_SPECULAR, PARTICLE_CONED_COSINE = 0, 1, 2
+BOUNDARY_REFLECTIVE, BOUNDARY_PERIODIC, BOUNDARY_IGNORE = 0, 1, 2
+
+EXPORTS = [
+    "vr_ctx_create", "vr_ctx_destroy", "vr_last_error", "vr_scene_set_disks",
+    "vr_scene_set_triangles", "vr_scene_set_boundary", "vr_scene_commit", "vr_trace",
+    "vr_trace_device", "vr_flux_device", "vr_flux_download", "vr_flux_download_fixed",
+    "vr_ctx_stream", "vr_ctx_synchronize", "vr_last_kernel_ms", "vr_build_neighbors", "vr_free",
+    "vr_debug_intersect", "vr_debug_source_rays", "vr_debug_math", "vr_debug_philox",
+    "vr_debug_reflect", "vr_debug_bvh_stats", "vr_debug_work_counters",
+]
+
+
+class SourceDesc(C.Structure):
+    _fields_ = [("bboxMin", C.c_float * 3), ("bboxMax", C.c_float * 3), ("rayDir", C.c_int32),
+                ("firstDir", C.c_int32), ("secondDir", C.c_int32), ("minMax", C.c_int32),
+                ("posNeg", C.c_float), ("useBasis", C.c_int32), ("basis", C.c_float * 9)]
+
+
+class ParticleDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("sticking", C.c_float), ("sourcePower", C.c_float),
+                ("coneMinAngle", C.c_float)]
+
+
+class Config(C.Structure):
+    _fields_ = [("numRays", C.c_uint64), ("rayIdxBegin", C.c_uint64), ("rayIdxEnd", C.c_uint64),
+                ("seed", C.c_uint32), ("maxReflections", C.c_uint32),
+                ("maxBoundaryHits", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class TraceInfo(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("numRays", "totalRaysTraced", "nonGeometryHits",
+                                          "geometryHits", "particleHits", "boundaryHits",
+                                          "reflections", "raysTerminated")] + [("time", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class VrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("viennaray_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "viennaray_b200: %s is missing -- build it with "
+                "`python -m viennaray_b200.build` (nvcc, sm_100a); there is no CPU fallback"
+                % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.vr_last_error.restype = C.c_char_p
+        L.vr_last_error.argtypes = [_vp]
+        L.vr_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
+        L.vr_ctx_destroy.restype = None
+        L.vr_ctx_destroy.argtypes = [_vp]
+        L.vr_scene_set_disks.argtypes = [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp]
+        L.vr_scene_set_triangles.argtypes = [_vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp]
+        L.vr_scene_set_boundary.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int]
+        L.vr_scene_commit.argtypes = [_vp]
+        L.vr_trace.argtypes = [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp]
+        L.vr_trace_device.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int]
+        L.vr_flux_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]
+        L.vr_flux_download.argtypes = [_vp, _vp, _vp]
+        L.vr_flux_download_fixed.argtypes = [_vp, _vp]
+        L.vr_ctx_stream.restype = _vp
+        L.vr_ctx_stream.argtypes = [_vp]
+        L.vr_ctx_synchronize.argtypes = [_vp]
+        L.vr_last_kernel_ms.restype = C.c_float
+        L.vr_last_kernel_ms.argtypes = [_vp]
+        L.vr_build_neighbors.argtypes = [C.c_int, _vp, C.c_uint32, C.c_float, C.POINTER(_vp),
+                                         C.POINTER(_vp)]
+        L.vr_free.restype = None
+        L.vr_free.argtypes = [_vp]
+        L.vr_debug_intersect.argtypes = [_vp, _vp, C.c_uint32, _vp, _vp, _vp, C.c_uint32, _vp, _vp]
+        L.vr_debug_source_rays.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp]
+        L.vr_debug_math.argtypes = [_vp, C.c_int, _vp, C.c_uint32, C.c_float, _vp]
+        L.vr_debug_philox.argtypes = [_vp] + [C.c_uint32] * 6 + [_vp]
+        L.vr_debug_reflect.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_float, C.c_uint32,
+                                       C.c_uint64, C.c_uint32, _vp]
+        L.vr_debug_bvh_stats.argtypes = [_vp, _vp]
+        L.vr_debug_work_counters.argtypes = [_vp, _vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def build_neighbors(D, points, distance):
+    """Neighbour CSR (offsets, indices) of PointNeighborhood::init semantics."""
+    L = lib()
+    points = np.ascontiguousarray(points, np.float32)
+    n = len(points)
+    off, idx = _vp(), _vp()
+    rc = L.vr_build_neighbors(D, _p(points), n, np.float32(distance), C.byref(off), C.byref(idx))
+    if rc:
+        raise VrError(rc, "vr_build_neighbors")
+    offsets = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_uint32)), (n + 1,)).copy()
+    total = int(offsets[-1])
+    indices = (np.ctypeslib.as_array(C.cast(idx, C.POINTER(C.c_uint32)), (total,)).copy()
+               if total else np.zeros(0, np.uint32))
+    L.vr_free(off)
+    L.vr_free(idx)
+    return offsets, indices
+
+
+class Context:
+    """One vr_ctx: one GPU, one scene."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        h = _vp()
+        rc = self.L.vr_ctx_create(device, C.byref(h))
+        if rc:
+            raise VrError(rc, self.L.vr_last_error(None).decode())
+        self.h = h
+        self.n = 0
+        self.num_particles = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vr_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc:
+            raise VrError(rc, self.L.vr_last_error(self.h).decode())
+
+    def set_disks(self, xyzr, normals, nb_offsets=None, nb_indices=None, material_ids=None):
+        xyzr = np.ascontiguousarray(xyzr, np.float32)
+        normals = np.ascontiguousarray(normals, np.float32)
+        assert xyzr.ndim == 2 and xyzr.shape[1] == 4 and normals.shape == (len(xyzr), 3)
+        if nb_offsets is not None:
+            nb_offsets = np.ascontiguousarray(nb_offsets, np.uint32)
+            nb_indices = np.ascontiguousarray(nb_indices, np.uint32)
+            if len(nb_indices) == 0:
+                nb_indices = np.zeros(1, np.uint32)
+        if material_ids is not None:
+            material_ids = np.ascontiguousarray(material_ids, np.int32)
+        self.n = len(xyzr)
+        self._ck(self.L.vr_scene_set_disks(self.h, _p(xyzr), _p(normals), self.n,
+                                           _p(material_ids), _p(nb_offsets), _p(nb_indices)))
+
+    def set_triangles(self, verts, tris, normals, material_ids=None):
+        verts = np.ascontiguousarray(verts, np.float32)
+        tris = np.ascontiguousarray(tris, np.uint32)
+        normals = np.ascontiguousarray(normals, np.float32)
+        if material_ids is not None:
+            material_ids = np.ascontiguousarray(material_ids, np.int32)
+        self.n = len(tris)
+        self._ck(self.L.vr_scene_set_triangles(self.h, _p(verts), len(verts), _p(tris), self.n,
+                                               _p(normals), _p(material_ids)))
+
+    def set_boundary(self, bbox_min, bbox_max, first_dir, second_dir, cond_first, cond_second, D):
+        lo = np.ascontiguousarray(bbox_min, np.float32)
+        hi = np.ascontiguousarray(bbox_max, np.float32)
+        self._ck(self.L.vr_scene_set_boundary(self.h, _p(lo), _p(hi), first_dir, second_dir,
+                                              cond_first, cond_second, D))
+
+    def commit(self):
+        self._ck(self.L.vr_scene_commit(self.h))
+
+    @staticmethod
+    def _particles(particles):
+        arr = (ParticleDesc * len(particles))()
+        for i, p in enumerate(particles):
+            arr[i] = p
+        return arr
+
+    def trace(self, source, particles, config):
+        """vr_trace: host in, host out.  Returns (flux[np, n] float64, infos)."""
+        np_ = len(particles)
+        flux = np.zeros((np_, self.n), np.float64)
+        infos = (TraceInfo * np_)()
+        arr = self._particles(particles)
+        self._ck(self.L.vr_trace(self.h, C.byref(source), arr, np_, C.byref(config), _p(flux),
+                                 infos))
+        self.num_particles = np_
+        return flux, list(infos)
+
+    def trace_device(self, source, particles, config, sync=False):
+        np_ = len(particles)
+        arr = self._particles(particles)
+        self._ck(self.L.vr_trace_device(self.h, C.byref(source), arr, np_, C.byref(config),
+                                        1 if sync else 0))
+        self.num_particles = np_
+
+    def flux_device(self):
+        ptr, words = _vp(), C.c_size_t()
+        self._ck(self.L.vr_flux_device(self.h, C.byref(ptr), C.byref(words)))
+        return ptr.value, words.value
+
+    def flux_download(self):
+        flux = np.zeros((self.num_particles, self.n), np.float64)
+        infos = (TraceInfo * self.num_particles)()
+        self._ck(self.L.vr_flux_download(self.h, _p(flux), infos))
+        return flux, list(infos)
+
+    def flux_download_fixed(self):
+        flux = np.zeros((self.num_particles, self.n), np.uint64)
+        self._ck(self.L.vr_flux_download_fixed(self.h, _p(flux)))
+        return flux
+
+    def stream(self):
+        return self.L.vr_ctx_stream(self.h)
+
+    def synchronize(self):
+        self._ck(self.L.vr_ctx_synchronize(self.h))
+
+    def last_kernel_ms(self):
+        return float(self.L.vr_last_kernel_ms(self.h))
+
+    def debug_intersect(self, rays, nb_cap=16):
+        rays = np.ascontiguousarray(rays, np.float32)
+        m = len(rays)
+        geom = np.zeros(m, np.uint32)
+        prim = np.zeros(m, np.uint32)
+        t = np.zeros(m, np.float32)
+        cnt = np.zeros(m, np.uint32)
+        nb = np.full((m, nb_cap), 0xFFFFFFFF, np.uint32)
+        self._ck(self.L.vr_debug_intersect(self.h, _p(rays), m, _p(geom), _p(prim), _p(t), nb_cap,
+                                           _p(cnt), _p(nb)))
+        return geom, prim, t, cnt, nb
+
+    def debug_source_rays(self, source, particle, config, idx_begin, m):
+        rays = np.zeros((m, 6), np.float32)
+        self._ck(self.L.vr_debug_source_rays(self.h, C.byref(source), C.byref(particle),
+                                             C.byref(config), idx_begin, m, _p(rays)))
+        return rays
+
+    def debug_math(self, which, x, param=0.0):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros(2 * len(x) if which == 0 else len(x), np.float32)
+        self._ck(self.L.vr_debug_math(self.h, which, _p(x), len(x), np.float32(param), _p(out)))
+        return out
+
+    def debug_philox(self, k0, k1, c0, c1, c2, c3):
+        out = np.zeros(4, np.uint32)
+        self._ck(self.L.vr_debug_philox(self.h, k0, k1, c0, c1, c2, c3, _p(out)))
+        return out
+
+    def debug_reflect(self, kind, D, ray_dir, normal, cone_min_angle, seed, idx, m):
+        rd = np.ascontiguousarray(ray_dir, np.float32)
+        nn = np.ascontiguousarray(normal, np.float32)
+        out = np.zeros((m, 3), np.float32)
+        self._ck(self.L.vr_debug_reflect(self.h, kind, D, _p(rd), _p(nn),
+                                         np.float32(cone_min_angle), seed, idx, m, _p(out)))
+        return out
+
+    def bvh_stats(self):
+        out = np.zeros(5, np.uint64)
+        self._ck(self.L.vr_debug_bvh_stats(self.h, _p(out)))
+        build_ms = np.array([out[4]], np.uint64).astype(np.uint32).view(np.float32)[0]
+        return {"nodes": int(out[0]), "leaves": int(out[1]), "max_leaf": int(out[2]),
+                "node_bytes": int(out[3]), "build_ms": float(build_ms)}
+
+    def work_counters(self):
+        out = np.zeros(4, np.uint64)
+        self._ck(self.L.vr_debug_work_counters(self.h, _p(out)))
+        return {"node_visits": int(out[0]), "prim_tests": int(out[1]), "nb_tests": int(out[2]),
+                "flux_adds": int(out[3])}

@@ -1,0 +1,797 @@
+// C ABI of the library (include/viennaray_b200.h): context, scene upload,
+// device BVH build, trace launches and result download.  Host-side C++ only
+// prepares buffers; all per-ray work runs in the sm_100a kernels of
+// vr_trace.cu.  No CPU fallback exists: every entry point needs a device.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vr_internal.h"
+
+using namespace vr;
+
+struct vr_ctx {
+  int device = 0;
+  int numSMs = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+
+  // host copy of the scene as set by the caller (original primitive order)
+  int geoType = -1;
+  uint32_t n = 0;
+  std::vector<float4> hA, hB, hC, hN;
+  std::vector<uint32_t> hNbOff, hNbIdx;
+  std::vector<int32_t> materialIds;
+  float geoLo[3] = {0, 0, 0}, geoHi[3] = {0, 0, 0};
+  bool boundarySet = false;
+  int D = 3;
+
+  // device scene (internal = BVH order)
+  float4 *dA = nullptr, *dB = nullptr, *dC = nullptr, *dN = nullptr;
+  uint32_t *dNbOff = nullptr, *dNbIdx = nullptr;
+  Bvh bvh;
+  DeviceScene scene{};
+  bool committed = false;
+
+  // results of the last trace
+  unsigned long long *dResult = nullptr;  // np*n flux words + np*8 counters
+  unsigned long long *dFluxOrig = nullptr;
+  unsigned long long *dCursor = nullptr;
+  unsigned long long *dWork = nullptr;
+  size_t resultWords = 0;
+  int numParticles = 0;
+  uint64_t lastNumRays = 0;
+  float lastMs = 0.f;
+  int kernelLaunches = 0;
+  bool countWork = false;
+};
+
+static std::string g_createError;
+
+static int fail(vr_ctx *ctx, int code, const std::string &msg) {
+  if (ctx)
+    ctx->err = msg;
+  else
+    g_createError = msg;
+  return code;
+}
+static int failCuda(vr_ctx *ctx, cudaError_t e, const char *what) {
+  return fail(ctx, VR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return failCuda(ctx, e_, #call);                                                             \
+  } while (0)
+
+static void freeDeviceScene(vr_ctx *c) {
+  cudaFree(c->dA);
+  cudaFree(c->dB);
+  cudaFree(c->dC);
+  cudaFree(c->dN);
+  cudaFree(c->dNbOff);
+  cudaFree(c->dNbIdx);
+  c->dA = c->dB = c->dC = c->dN = nullptr;
+  c->dNbOff = c->dNbIdx = nullptr;
+  freeBvh(&c->bvh);
+  c->committed = false;
+}
+static void freeResults(vr_ctx *c) {
+  cudaFree(c->dResult);
+  cudaFree(c->dFluxOrig);
+  c->dResult = c->dFluxOrig = nullptr;
+  c->resultWords = 0;
+  c->numParticles = 0;
+}
+
+extern "C" {
+
+const char *vr_last_error(const vr_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_createError.c_str();
+}
+
+int vr_ctx_create(int cudaDevice, vr_ctx **out) {
+  if (!out)
+    return fail(nullptr, VR_ERR_ARGUMENT, "vr_ctx_create: out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, VR_ERR_CUDA,
+                std::string("vr_ctx_create: no CUDA device (") + cudaGetErrorString(e) +
+                    "); this library has no CPU path");
+  if (cudaDevice < 0 || cudaDevice >= count)
+    return fail(nullptr, VR_ERR_ARGUMENT, "vr_ctx_create: device index out of range");
+  e = cudaSetDevice(cudaDevice);
+  if (e != cudaSuccess)
+    return failCuda(nullptr, e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, cudaDevice);
+  if (e != cudaSuccess)
+    return failCuda(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major < 10)
+    return fail(nullptr, VR_ERR_CUDA,
+                "vr_ctx_create: kernels are built for sm_100a only; device is sm_" +
+                    std::to_string(prop.major * 10 + prop.minor));
+  vr_ctx *ctx = new vr_ctx();
+  ctx->device = cudaDevice;
+  ctx->numSMs = prop.multiProcessorCount;
+  const char *cw = getenv("VR_COUNT_WORK");
+  ctx->countWork = cw && cw[0] == '1';
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->dCursor, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->dWork, 4 * sizeof(unsigned long long))) != cudaSuccess) {
+    failCuda(nullptr, e, "vr_ctx_create");
+    vr_ctx_destroy(ctx);
+    return VR_ERR_CUDA;
+  }
+  *out = ctx;
+  return VR_OK;
+}
+
+void vr_ctx_destroy(vr_ctx *ctx) {
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  freeDeviceScene(ctx);
+  freeResults(ctx);
+  cudaFree(ctx->dCursor);
+  cudaFree(ctx->dWork);
+  if (ctx->ev0)
+    cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1)
+    cudaEventDestroy(ctx->ev1);
+  if (ctx->stream)
+    cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void *vr_ctx_stream(vr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int vr_ctx_synchronize(vr_ctx *ctx) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VR_OK;
+}
+float vr_last_kernel_ms(vr_ctx *ctx) { return ctx ? ctx->lastMs : 0.f; }
+
+int vr_scene_set_disks(vr_ctx *ctx, const float *xyzr, const float *nxyz, uint32_t n,
+                       const int32_t *materialIds, const uint32_t *nbOffsets,
+                       const uint32_t *nbIndices) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  if (!xyzr || !nxyz || n == 0)
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_disks: no geometry was passed");
+  if (n >= (1u << 27))
+    return fail(ctx, VR_ERR_UNSUPPORTED, "vr_scene_set_disks: more than 2^27 primitives");
+  if ((nbOffsets == nullptr) != (nbIndices == nullptr) && nbOffsets && nbOffsets[n] != 0)
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_disks: nbOffsets without nbIndices");
+  ctx->committed = false;
+  ctx->geoType = 0;
+  ctx->n = n;
+  ctx->hA.resize(n);
+  ctx->hB.resize(n);
+  ctx->hC.clear();
+  ctx->hN.clear();
+  for (int a = 0; a < 3; ++a) {
+    ctx->geoLo[a] = INFINITY;
+    ctx->geoHi[a] = -INFINITY;
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    ctx->hA[i] = make_float4(xyzr[4 * i], xyzr[4 * i + 1], xyzr[4 * i + 2], xyzr[4 * i + 3]);
+    float4 nn = make_float4(nxyz[3 * i], nxyz[3 * i + 1], nxyz[3 * i + 2], 0.f);
+    memcpy(&nn.w, &i, 4);  // original primitive ID rides in .w
+    ctx->hB[i] = nn;
+    for (int a = 0; a < 3; ++a) {
+      float r = xyzr[4 * i + 3], v = xyzr[4 * i + a];
+      ctx->geoLo[a] = std::min(ctx->geoLo[a], v - r);
+      ctx->geoHi[a] = std::max(ctx->geoHi[a], v + r);
+    }
+  }
+  if (nbOffsets) {
+    ctx->hNbOff.assign(nbOffsets, nbOffsets + n + 1);
+    if (nbOffsets[0] != 0)
+      return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_disks: nbOffsets[0] must be 0");
+    for (uint32_t i = 0; i < n; ++i)
+      if (nbOffsets[i + 1] < nbOffsets[i])
+        return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_disks: nbOffsets not monotone");
+    ctx->hNbIdx.assign(nbIndices, nbIndices + nbOffsets[n]);
+    for (uint32_t v : ctx->hNbIdx)
+      if (v >= n)
+        return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_disks: neighbour index out of range");
+  } else {
+    ctx->hNbOff.assign(n + 1, 0u);
+    ctx->hNbIdx.clear();
+  }
+  if (materialIds)
+    ctx->materialIds.assign(materialIds, materialIds + n);
+  else
+    ctx->materialIds.assign(n, 0);
+  return VR_OK;
+}
+
+int vr_scene_set_triangles(vr_ctx *ctx, const float *verts, uint32_t nVerts, const uint32_t *idx,
+                           uint32_t n, const float *normals, const int32_t *materialIds) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  if (!verts || !idx || !normals || n == 0 || nVerts == 0)
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_triangles: no geometry was passed");
+  if (n >= (1u << 27))
+    return fail(ctx, VR_ERR_UNSUPPORTED, "vr_scene_set_triangles: more than 2^27 primitives");
+  ctx->committed = false;
+  ctx->geoType = 1;
+  ctx->n = n;
+  ctx->hA.resize(n);
+  ctx->hB.resize(n);
+  ctx->hC.resize(n);
+  ctx->hN.resize(n);
+  for (int a = 0; a < 3; ++a) {
+    ctx->geoLo[a] = INFINITY;
+    ctx->geoHi[a] = -INFINITY;
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    float w;
+    memcpy(&w, &i, 4);
+    for (int k = 0; k < 3; ++k) {
+      uint32_t v = idx[3 * i + k];
+      if (v >= nVerts)
+        return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_triangles: vertex index out of range");
+      float4 p = make_float4(verts[3 * v], verts[3 * v + 1], verts[3 * v + 2], w);
+      (k == 0 ? ctx->hA : (k == 1 ? ctx->hB : ctx->hC))[i] = p;
+      ctx->geoLo[0] = std::min(ctx->geoLo[0], p.x);
+      ctx->geoLo[1] = std::min(ctx->geoLo[1], p.y);
+      ctx->geoLo[2] = std::min(ctx->geoLo[2], p.z);
+      ctx->geoHi[0] = std::max(ctx->geoHi[0], p.x);
+      ctx->geoHi[1] = std::max(ctx->geoHi[1], p.y);
+      ctx->geoHi[2] = std::max(ctx->geoHi[2], p.z);
+    }
+    ctx->hN[i] = make_float4(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2], w);
+  }
+  ctx->hNbOff.assign(n + 1, 0u);
+  ctx->hNbIdx.clear();
+  if (materialIds)
+    ctx->materialIds.assign(materialIds, materialIds + n);
+  else
+    ctx->materialIds.assign(n, 0);
+  return VR_OK;
+}
+
+int vr_scene_set_boundary(vr_ctx *ctx, const float bboxMin[3], const float bboxMax[3],
+                          int firstDir, int secondDir, int condFirst, int condSecond, int D) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  if (!bboxMin || !bboxMax || (D != 2 && D != 3) || firstDir < 0 || firstDir > 2 ||
+      secondDir < 0 || secondDir > 2 || firstDir == secondDir || condFirst < 0 || condFirst > 2 ||
+      condSecond < 0 || condSecond > 2)
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_boundary: invalid argument");
+  DeviceScene &s = ctx->scene;
+  ctx->D = D;
+  s.D = D;
+  for (int a = 0; a < 3; ++a) {
+    s.bbox[0][a] = bboxMin[a];
+    s.bbox[1][a] = bboxMax[a];
+  }
+  s.firstDir = firstDir;
+  s.secondDir = secondDir;
+  s.bc[0] = condFirst;
+  s.bc[1] = condSecond;
+  // vertex and triangle tables of Boundary::initBoundary, rayBoundary.hpp:182-233
+  float v[8][3];
+  for (int k = 0; k < 8; ++k) {
+    int xi = (k == 1 || k == 2 || k == 5 || k == 6), yi = (k == 2 || k == 3 || k == 6 || k == 7),
+        zi = k >= 4;
+    v[k][0] = s.bbox[xi][0];
+    v[k][1] = s.bbox[yi][1];
+    v[k][2] = s.bbox[zi][2];
+  }
+  static const int planes[3][4][3] = {{{0, 3, 7}, {0, 7, 4}, {6, 2, 1}, {6, 1, 5}},
+                                      {{0, 4, 5}, {0, 5, 1}, {6, 7, 3}, {6, 3, 2}},
+                                      {{0, 1, 2}, {0, 2, 3}, {6, 5, 4}, {6, 4, 7}}};
+  for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < 3; ++k)
+      for (int a = 0; a < 3; ++a) {
+        s.btri[i][k][a] = v[planes[firstDir][i][k]][a];
+        s.btri[i + 4][k][a] = v[planes[secondDir][i][k]][a];
+      }
+  ctx->boundarySet = true;
+  return VR_OK;
+}
+
+int vr_scene_commit(vr_ctx *ctx) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  if (ctx->geoType < 0)
+    return fail(ctx, VR_ERR_STATE, "vr_scene_commit: no geometry was passed");
+  if (!ctx->boundarySet)
+    return fail(ctx, VR_ERR_STATE, "vr_scene_commit: no boundary was set");
+  CK(cudaSetDevice(ctx->device));
+  freeDeviceScene(ctx);
+  const uint32_t n = ctx->n;
+  const bool tri = ctx->geoType == 1;
+  // 1. original-order primitives to the device, padded boxes, BVH
+  float4 *oA = nullptr, *oB = nullptr, *oC = nullptr, *lo = nullptr, *hi = nullptr;
+  auto tmpFree = [&]() {
+    cudaFree(oA);
+    cudaFree(oB);
+    cudaFree(oC);
+    cudaFree(lo);
+    cudaFree(hi);
+  };
+#define CKT(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      tmpFree();                                                                                   \
+      return failCuda(ctx, e_, #call);                                                             \
+    }                                                                                              \
+  } while (0)
+  const size_t bytes = sizeof(float4) * n;
+  CKT(cudaMalloc(&oA, bytes));
+  CKT(cudaMalloc(&oB, bytes));
+  CKT(cudaMalloc(&lo, bytes));
+  CKT(cudaMalloc(&hi, bytes));
+  CKT(cudaMemcpyAsync(oA, ctx->hA.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CKT(cudaMemcpyAsync(oB, ctx->hB.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (tri) {
+    CKT(cudaMalloc(&oC, bytes));
+    CKT(cudaMemcpyAsync(oC, ctx->hC.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CKT(launchTriBounds(oA, oB, oC, n, lo, hi, ctx->stream));
+  } else {
+    CKT(launchDiskBounds(oA, oB, n, lo, hi, ctx->stream));
+  }
+  CKT(buildBvh(lo, hi, n, ctx->geoLo, ctx->geoHi, ctx->stream, &ctx->bvh));
+  tmpFree();
+#undef CKT
+  // 2. primitives and neighbour lists in BVH order (internal index space)
+  std::vector<uint32_t> s2o(n), o2s(n);
+  CK(cudaMemcpy(s2o.data(), ctx->bvh.sortedToOrig, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n; ++i)
+    o2s[s2o[i]] = i;
+  std::vector<float4> sA(n), sB(n), sC, sN;
+  if (tri) {
+    sC.resize(n);
+    sN.resize(n);
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t o = s2o[i];
+    sA[i] = ctx->hA[o];
+    sB[i] = ctx->hB[o];
+    if (tri) {
+      sC[i] = ctx->hC[o];
+      sN[i] = ctx->hN[o];
+    }
+  }
+  std::vector<uint32_t> off(n + 1, 0u), idx(ctx->hNbIdx.size());
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t o = s2o[i];
+    off[i + 1] = off[i] + (ctx->hNbOff[o + 1] - ctx->hNbOff[o]);
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t o = s2o[i], w = off[i];
+    for (uint32_t k = ctx->hNbOff[o]; k < ctx->hNbOff[o + 1]; ++k)
+      idx[w++] = o2s[ctx->hNbIdx[k]];
+  }
+  CK(cudaMalloc(&ctx->dA, bytes));
+  CK(cudaMalloc(&ctx->dB, bytes));
+  CK(cudaMemcpy(ctx->dA, sA.data(), bytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dB, sB.data(), bytes, cudaMemcpyHostToDevice));
+  if (tri) {
+    CK(cudaMalloc(&ctx->dC, bytes));
+    CK(cudaMalloc(&ctx->dN, bytes));
+    CK(cudaMemcpy(ctx->dC, sC.data(), bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->dN, sN.data(), bytes, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMalloc(&ctx->dNbOff, sizeof(uint32_t) * (n + 1)));
+  CK(cudaMalloc(&ctx->dNbIdx, sizeof(uint32_t) * std::max<size_t>(idx.size(), 1)));
+  CK(cudaMemcpy(ctx->dNbOff, off.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice));
+  if (!idx.empty())
+    CK(cudaMemcpy(ctx->dNbIdx, idx.data(), sizeof(uint32_t) * idx.size(),
+                  cudaMemcpyHostToDevice));
+  DeviceScene &s = ctx->scene;
+  s.geoType = ctx->geoType;
+  s.numPrims = n;
+  s.primA = ctx->dA;
+  s.primB = ctx->dB;
+  s.primC = ctx->dC;
+  s.primN = tri ? ctx->dN : ctx->dB;
+  s.nbOff = ctx->dNbOff;
+  s.nbIdx = ctx->dNbIdx;
+  s.nodes = ctx->bvh.nodes;
+  s.rootRef = ctx->bvh.rootRef;
+  ctx->committed = true;
+  return VR_OK;
+}
+
+static int fillParams(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_desc *part,
+                      const vr_config *cfg, int particleIndex, TraceParams &p) {
+  if (!src || !part || !cfg)
+    return fail(ctx, VR_ERR_ARGUMENT, "trace: null descriptor");
+  if (part->kind < 0 || part->kind > VR_PARTICLE_CONED_COSINE)
+    return fail(ctx, VR_ERR_UNSUPPORTED,
+                "trace: unknown particle kind; only the built-in particles run on the device");
+  if (src->rayDir < 0 || src->rayDir > 2 || src->firstDir < 0 || src->firstDir > 2 ||
+      src->secondDir < 0 || src->secondDir > 2)
+    return fail(ctx, VR_ERR_ARGUMENT, "trace: invalid source axes");
+  if (ctx->D == 2 && src->rayDir == 2)
+    return fail(ctx, VR_ERR_ARGUMENT, "trace: invalid source direction in 2D geometry");
+  if (cfg->rayIdxEnd < cfg->rayIdxBegin || cfg->rayIdxEnd > cfg->numRays)
+    return fail(ctx, VR_ERR_ARGUMENT, "trace: ray index shard out of range");
+  p.scene = ctx->scene;
+  p.src = *src;
+  p.particle = *part;
+  p.ee = 1.0f / (part->sourcePower + 1.0f);
+  p.idxBegin = cfg->rayIdxBegin;
+  p.idxEnd = cfg->rayIdxEnd;
+  p.seed = cfg->seed;
+  p.stream = (uint32_t)particleIndex;
+  p.maxReflections = cfg->maxReflections;
+  p.maxBoundaryHits = cfg->maxBoundaryHits;
+  p.rayCursor = ctx->dCursor;
+  p.work = ctx->countWork ? ctx->dWork : nullptr;
+  return VR_OK;
+}
+
+int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_desc *particles,
+                    int np, const vr_config *cfg, int sync) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  if (!ctx->committed)
+    return fail(ctx, VR_ERR_STATE, "trace: scene not committed");
+  if (np < 1 || !particles)
+    return fail(ctx, VR_ERR_ARGUMENT, "trace: no particle was specified");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = ctx->n;
+  const size_t words = (size_t)np * n + (size_t)np * 8;
+  if (words != ctx->resultWords) {
+    freeResults(ctx);
+    CK(cudaMalloc(&ctx->dResult, sizeof(unsigned long long) * words));
+    CK(cudaMalloc(&ctx->dFluxOrig, sizeof(unsigned long long) * (size_t)np * n));
+    ctx->resultWords = words;
+  }
+  ctx->numParticles = np;
+  ctx->lastNumRays = cfg ? cfg->rayIdxEnd - cfg->rayIdxBegin : 0;
+  CK(cudaMemsetAsync(ctx->dResult, 0, sizeof(unsigned long long) * words, ctx->stream));
+  if (ctx->countWork)
+    CK(cudaMemsetAsync(ctx->dWork, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  ctx->kernelLaunches = 0;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int k = 0; k < np; ++k) {
+    TraceParams p;
+    int rc = fillParams(ctx, src, &particles[k], cfg, k, p);
+    if (rc)
+      return rc;
+    p.flux = ctx->dResult + (size_t)k * n;
+    p.counters = ctx->dResult + (size_t)np * n + (size_t)k * 8;
+    CK(cudaMemsetAsync(ctx->dCursor, 0, sizeof(unsigned long long), ctx->stream));
+    if (p.idxEnd > p.idxBegin)
+      CK(launchTrace(p, ctx->numSMs, ctx->stream, &ctx->kernelLaunches));
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (sync) {
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(&ctx->lastMs, ctx->ev0, ctx->ev1));
+  }
+  return VR_OK;
+}
+
+int vr_flux_device(vr_ctx *ctx, void **devicePtr, size_t *numWords) {
+  if (!ctx || !devicePtr || !numWords)
+    return VR_ERR_ARGUMENT;
+  if (!ctx->dResult)
+    return fail(ctx, VR_ERR_STATE, "vr_flux_device: no trace has run");
+  *devicePtr = ctx->dResult;
+  *numWords = ctx->resultWords;
+  return VR_OK;
+}
+
+static int downloadFixed(vr_ctx *ctx, std::vector<unsigned long long> &flux,
+                         std::vector<unsigned long long> &counters) {
+  if (!ctx->dResult)
+    return fail(ctx, VR_ERR_STATE, "download: no trace has run");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = ctx->n, np = ctx->numParticles;
+  for (size_t k = 0; k < np; ++k)
+    CK(launchUnsortFlux(ctx->dResult + k * n, ctx->bvh.sortedToOrig, (uint32_t)n,
+                        ctx->dFluxOrig + k * n, ctx->stream));
+  flux.resize(np * n);
+  counters.resize(np * 8);
+  CK(cudaMemcpyAsync(flux.data(), ctx->dFluxOrig, sizeof(unsigned long long) * np * n,
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(counters.data(), ctx->dResult + np * n, sizeof(unsigned long long) * np * 8,
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (cudaEventQuery(ctx->ev1) == cudaSuccess)
+    cudaEventElapsedTime(&ctx->lastMs, ctx->ev0, ctx->ev1);
+  return VR_OK;
+}
+
+int vr_flux_download(vr_ctx *ctx, double *fluxOut, vr_trace_info *infoOut) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  std::vector<unsigned long long> flux, counters;
+  int rc = downloadFixed(ctx, flux, counters);
+  if (rc)
+    return rc;
+  if (fluxOut)
+    for (size_t i = 0; i < flux.size(); ++i)
+      fluxOut[i] = (double)flux[i] * (1.0 / VR_FLUX_FIXED_SCALE);
+  if (infoOut)
+    for (int k = 0; k < ctx->numParticles; ++k) {
+      const unsigned long long *c = &counters[(size_t)k * 8];
+      vr_trace_info &ti = infoOut[k];
+      ti.numRays = ctx->lastNumRays;
+      ti.totalRaysTraced = c[1];
+      ti.nonGeometryHits = c[2];
+      ti.geometryHits = c[3];
+      ti.particleHits = c[4];
+      ti.boundaryHits = c[5];
+      ti.reflections = c[6];
+      ti.raysTerminated = c[7];
+      ti.time = (double)ctx->lastMs * 1e-3;
+    }
+  return VR_OK;
+}
+
+int vr_flux_download_fixed(vr_ctx *ctx, uint64_t *fluxOut) {
+  if (!ctx || !fluxOut)
+    return VR_ERR_ARGUMENT;
+  std::vector<unsigned long long> flux, counters;
+  int rc = downloadFixed(ctx, flux, counters);
+  if (rc)
+    return rc;
+  memcpy(fluxOut, flux.data(), sizeof(uint64_t) * flux.size());
+  return VR_OK;
+}
+
+int vr_trace(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_desc *particles, int np,
+             const vr_config *cfg, double *fluxOut, vr_trace_info *infoOut) {
+  int rc = vr_trace_device(ctx, src, particles, np, cfg, 1);
+  if (rc)
+    return rc;
+  return vr_flux_download(ctx, fluxOut, infoOut);
+}
+
+// ---- host-side geometry helper ---------------------------------------------
+int vr_build_neighbors(int D, const float *pts, uint32_t n, float dist, uint32_t **offOut,
+                       uint32_t **idxOut) {
+  if (!pts || !offOut || !idxOut || (D != 2 && D != 3))
+    return VR_ERR_ARGUMENT;
+  uint32_t *off = (uint32_t *)calloc((size_t)n + 1, sizeof(uint32_t));
+  *offOut = off;
+  *idxOut = nullptr;
+  if (n == 0 || !(dist > 0.f)) {
+    *idxOut = (uint32_t *)malloc(sizeof(uint32_t));
+    return VR_OK;
+  }
+  // uniform grid of cell size >= dist over the first D axes, points sorted by cell
+  float lo[3] = {INFINITY, INFINITY, INFINITY};
+  for (uint32_t i = 0; i < n; ++i)
+    for (int a = 0; a < D; ++a)
+      lo[a] = std::min(lo[a], pts[3 * i + a]);
+  const float cell = dist * 1.0001f;
+  auto cellOf = [&](const float *p, int a) -> int64_t {
+    return a < D ? (int64_t)std::floor((p[a] - lo[a]) / cell) + 1 : 1;
+  };
+  auto keyOf = [](int64_t x, int64_t y, int64_t z) -> uint64_t {
+    return ((uint64_t)x & 0x1fffff) | (((uint64_t)y & 0x1fffff) << 21) |
+           (((uint64_t)z & 0x1fffff) << 42);
+  };
+  std::vector<std::pair<uint64_t, uint32_t>> refs(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    const float *p = pts + 3 * i;
+    refs[i] = {keyOf(cellOf(p, 0), cellOf(p, 1), cellOf(p, 2)), i};
+  }
+  std::sort(refs.begin(), refs.end());
+  const float dist2 = dist * dist;
+  auto isNb = [&](const float *p, const float *q) {
+    for (int a = 0; a < D; ++a)
+      if (std::fabs(p[a] - q[a]) > dist)
+        return false;
+    float dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+    return (dx * dx + dy * dy) + dz * dz <= dist2;
+  };
+  std::vector<std::vector<uint32_t>> rows(n);
+  const int zr = D == 3 ? 1 : 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const float *p = pts + 3 * i;
+    int64_t cx = cellOf(p, 0), cy = cellOf(p, 1), cz = cellOf(p, 2);
+    for (int dz = -zr; dz <= zr; ++dz)
+      for (int dy = -1; dy <= 1; ++dy) {
+        // the three x-cells are consecutive keys: one range scan
+        uint64_t k0 = keyOf(cx - 1, cy + dy, cz + dz), k1 = keyOf(cx + 1, cy + dy, cz + dz);
+        auto it = std::lower_bound(refs.begin(), refs.end(), std::make_pair(k0, 0u));
+        for (; it != refs.end() && it->first <= k1; ++it) {
+          uint32_t j = it->second;
+          if (j != i && isNb(p, pts + 3 * j))
+            rows[i].push_back(j);
+        }
+      }
+    std::sort(rows[i].begin(), rows[i].end());
+  }
+  for (uint32_t i = 0; i < n; ++i)
+    off[i + 1] = off[i] + (uint32_t)rows[i].size();
+  uint32_t *idx = (uint32_t *)malloc(sizeof(uint32_t) * std::max<size_t>(off[n], 1));
+  for (uint32_t i = 0; i < n; ++i)
+    std::copy(rows[i].begin(), rows[i].end(), idx + off[i]);
+  *idxOut = idx;
+  return VR_OK;
+}
+
+void vr_free(void *p) { free(p); }
+
+// ---- parity / debugging ------------------------------------------------------
+int vr_debug_intersect(vr_ctx *ctx, const float *rays, uint32_t m, uint32_t *geomOut,
+                       uint32_t *primOut, float *tOut, uint32_t nbCap, uint32_t *nbCountOut,
+                       uint32_t *nbOut) {
+  if (!ctx || !rays || !geomOut || !primOut || !tOut)
+    return VR_ERR_ARGUMENT;
+  if (!ctx->committed)
+    return fail(ctx, VR_ERR_STATE, "vr_debug_intersect: scene not committed");
+  CK(cudaSetDevice(ctx->device));
+  float *dRays = nullptr, *dT = nullptr;
+  uint32_t *dGeom = nullptr, *dPrim = nullptr, *dCnt = nullptr, *dNb = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(dRays);
+    cudaFree(dT);
+    cudaFree(dGeom);
+    cudaFree(dPrim);
+    cudaFree(dCnt);
+    cudaFree(dNb);
+  };
+#define CKD(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      cleanup();                                                                                   \
+      return failCuda(ctx, e_, #call);                                                             \
+    }                                                                                              \
+  } while (0)
+  const bool wantNb = nbCountOut && nbOut && nbCap;
+  CKD(cudaMalloc(&dRays, sizeof(float) * 6 * (size_t)m + 16));
+  CKD(cudaMalloc(&dT, sizeof(float) * m + 16));
+  CKD(cudaMalloc(&dGeom, sizeof(uint32_t) * m + 16));
+  CKD(cudaMalloc(&dPrim, sizeof(uint32_t) * m + 16));
+  if (wantNb) {
+    CKD(cudaMalloc(&dCnt, sizeof(uint32_t) * m + 16));
+    CKD(cudaMalloc(&dNb, sizeof(uint32_t) * (size_t)m * nbCap + 16));
+    CKD(cudaMemsetAsync(dNb, 0xff, sizeof(uint32_t) * (size_t)m * nbCap, ctx->stream));
+  }
+  CKD(cudaMemcpyAsync(dRays, rays, sizeof(float) * 6 * (size_t)m, cudaMemcpyHostToDevice,
+                      ctx->stream));
+  CKD(launchDebugIntersect(ctx->scene, dRays, m, dGeom, dPrim, dT, nbCap, dCnt, dNb,
+                           ctx->bvh.sortedToOrig, ctx->stream));
+  CKD(cudaMemcpyAsync(geomOut, dGeom, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+  CKD(cudaMemcpyAsync(primOut, dPrim, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+  CKD(cudaMemcpyAsync(tOut, dT, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));
+  if (wantNb) {
+    CKD(cudaMemcpyAsync(nbCountOut, dCnt, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost,
+                        ctx->stream));
+    CKD(cudaMemcpyAsync(nbOut, dNb, sizeof(uint32_t) * (size_t)m * nbCap, cudaMemcpyDeviceToHost,
+                        ctx->stream));
+  }
+  CKD(cudaStreamSynchronize(ctx->stream));
+  cleanup();
+  return VR_OK;
+}
+
+int vr_debug_source_rays(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_desc *part,
+                         const vr_config *cfg, uint64_t idxBegin, uint32_t m, float *raysOut) {
+  if (!ctx || !raysOut)
+    return VR_ERR_ARGUMENT;
+  if (!ctx->boundarySet)
+    return fail(ctx, VR_ERR_STATE, "vr_debug_source_rays: no boundary was set");
+  CK(cudaSetDevice(ctx->device));
+  TraceParams p;
+  int rc = fillParams(ctx, src, part, cfg, 0, p);
+  if (rc)
+    return rc;
+  float *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(float) * 6 * (size_t)m + 16));
+  cudaError_t e = launchDebugSourceRays(p, idxBegin, m, d, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(raysOut, d, sizeof(float) * 6 * (size_t)m, cudaMemcpyDeviceToHost,
+                        ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess)
+    return failCuda(ctx, e, "vr_debug_source_rays");
+  return VR_OK;
+}
+
+int vr_debug_math(vr_ctx *ctx, int which, const float *x, uint32_t m, float param, float *out) {
+  if (!ctx || !x || !out || which < 0 || which > 2)
+    return VR_ERR_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  const size_t outN = which == 0 ? 2 * (size_t)m : m;
+  float *dx = nullptr, *dout = nullptr;
+  CK(cudaMalloc(&dx, sizeof(float) * m + 16));
+  cudaError_t e = cudaMalloc(&dout, sizeof(float) * outN + 16);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(dx, x, sizeof(float) * m, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = launchDebugMath(which, dx, m, param, dout, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out, dout, sizeof(float) * outN, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dx);
+  cudaFree(dout);
+  if (e != cudaSuccess)
+    return failCuda(ctx, e, "vr_debug_math");
+  return VR_OK;
+}
+
+int vr_debug_philox(vr_ctx *ctx, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                    uint32_t c3, uint32_t *out4) {
+  if (!ctx || !out4)
+    return VR_ERR_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  uint32_t *d = nullptr;
+  CK(cudaMalloc(&d, 16));
+  cudaError_t e = launchDebugPhilox(k0, k1, c0, c1, c2, c3, d, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out4, d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess)
+    return failCuda(ctx, e, "vr_debug_philox");
+  return VR_OK;
+}
+
+int vr_debug_reflect(vr_ctx *ctx, int kind, int D, const float *rayDir, const float *normal,
+                     float coneMinAngle, uint32_t seed, uint64_t idx, uint32_t m, float *out3) {
+  if (!ctx || !rayDir || !normal || !out3 || (D != 2 && D != 3) || kind < 0 || kind > 2)
+    return VR_ERR_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  float *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(float) * 3 * (size_t)m + 16));
+  cudaError_t e =
+      launchDebugReflect(kind, D, rayDir, normal, coneMinAngle, seed, idx, m, d, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out3, d, sizeof(float) * 3 * (size_t)m, cudaMemcpyDeviceToHost,
+                        ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess)
+    return failCuda(ctx, e, "vr_debug_reflect");
+  return VR_OK;
+}
+
+int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out5) {
+  if (!ctx || !out5)
+    return VR_ERR_ARGUMENT;
+  if (!ctx->committed)
+    return fail(ctx, VR_ERR_STATE, "vr_debug_bvh_stats: scene not committed");
+  out5[0] = ctx->bvh.numNodes;
+  out5[1] = ctx->bvh.numLeaves;
+  out5[2] = ctx->bvh.maxLeaf;
+  out5[3] = sizeof(Node2);
+  uint32_t bits;
+  memcpy(&bits, &ctx->bvh.buildMs, 4);
+  out5[4] = bits;
+  return VR_OK;
+}
+
+int vr_debug_work_counters(vr_ctx *ctx, uint64_t *out4) {
+  if (!ctx || !out4)
+    return VR_ERR_ARGUMENT;
+  if (!ctx->countWork)
+    return fail(ctx, VR_ERR_STATE, "vr_debug_work_counters: set VR_COUNT_WORK=1 before create");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out4, ctx->dWork, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return VR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// Device-side construction of the acceleration structure; replaces Embree's
+// rtcJoinCommitScene (rayTraceKernel.hpp:91).
+//
+//   1. 63-bit Morton code of every primitive's box centre
+//   2. radix sort (CUB) of (code, primitive)
+//   3. Karras-2012 binary radix tree over the sorted codes, one thread per
+//      internal node; index bits break ties between equal codes
+//   4. bottom-up refit of node boxes with one atomic flag per node
+//   5. emission of 64-byte nodes holding both child boxes; subtrees of at
+//      most VR_LEAF_MAX primitives become leaves (contiguous sorted ranges)
+#include <cub/device/device_radix_sort.cuh>
+
+#include "vr_internal.h"
+
+namespace vr {
+
+namespace {
+
+__device__ __forceinline__ unsigned long long expandBits21(unsigned long long v) {
+  v &= 0x1fffffull;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void mortonKernel(const float4 *lo, const float4 *hi, uint32_t n, float3 sLo,
+                             float3 sInv, unsigned long long *keys, uint32_t *vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  float4 l = lo[i], h = hi[i];
+  float cx = (0.5f * (l.x + h.x) - sLo.x) * sInv.x;
+  float cy = (0.5f * (l.y + h.y) - sLo.y) * sInv.y;
+  float cz = (0.5f * (l.z + h.z) - sLo.z) * sInv.z;
+  const float S = 2097151.f;
+  unsigned long long x = (unsigned long long)fminf(fmaxf(cx * S, 0.f), S);
+  unsigned long long y = (unsigned long long)fminf(fmaxf(cy * S, 0.f), S);
+  unsigned long long z = (unsigned long long)fminf(fmaxf(cz * S, 0.f), S);
+  keys[i] = (expandBits21(x) << 2) | (expandBits21(y) << 1) | expandBits21(z);
+  vals[i] = i;
+}
+
+// length of the common prefix of (key_i, i) and (key_j, j); -1 out of range
+__device__ __forceinline__ int delta(const unsigned long long *keys, int n, int i, int j) {
+  if (j < 0 || j >= n)
+    return -1;
+  unsigned long long a = keys[i], b = keys[j];
+  if (a != b)
+    return __clzll((long long)(a ^ b));
+  return 64 + __clz(i ^ j);
+}
+
+// Karras 2012: internal node i covers [first,last]; children are split, split+1
+__global__ void radixTreeKernel(const unsigned long long *keys, int n, int2 *range, int *split,
+                                int *parentOfInternal, int *parentOfLeaf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+  int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dMin = delta(keys, n, i, i - d);
+  int lMax = 2;
+  while (delta(keys, n, i, i + lMax * d) > dMin)
+    lMax <<= 1;
+  int l = 0;
+  for (int t = lMax >> 1; t >= 1; t >>= 1)
+    if (delta(keys, n, i, i + (l + t) * d) > dMin)
+      l += t;
+  int j = i + l * d;
+  int dNode = delta(keys, n, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta(keys, n, i, i + (s + t) * d) > dNode)
+      s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int first = min(i, j), last = max(i, j);
+  range[i] = make_int2(first, last);
+  split[i] = gamma;
+  if (first == gamma)
+    parentOfLeaf[gamma] = i;
+  else
+    parentOfInternal[gamma] = i;
+  if (last == gamma + 1)
+    parentOfLeaf[gamma + 1] = i;
+  else
+    parentOfInternal[gamma + 1] = i;
+  if (i == 0)
+    parentOfInternal[0] = -1;
+}
+
+__global__ void refitKernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
+                            const int2 *range, const int *split, const int *parentOfInternal,
+                            const int *parentOfLeaf, float4 *nodeLo, float4 *nodeHi, int *flags) {
+  int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n)
+    return;
+  int node = parentOfLeaf[leaf];
+  while (node >= 0) {
+    if (atomicAdd(&flags[node], 1) == 0)
+      return;  // the sibling subtree finishes this node
+    __threadfence();
+    int g = split[node];
+    int2 r = range[node];
+    float4 l0, h0, l1, h1;
+    if (r.x == g) {
+      uint32_t p = sorted[g];
+      l0 = lo[p];
+      h0 = hi[p];
+    } else {
+      l0 = __ldcg(&nodeLo[g]);  // written by another SM: read through L2
+      h0 = __ldcg(&nodeHi[g]);
+    }
+    if (r.y == g + 1) {
+      uint32_t p = sorted[g + 1];
+      l1 = lo[p];
+      h1 = hi[p];
+    } else {
+      l1 = __ldcg(&nodeLo[g + 1]);
+      h1 = __ldcg(&nodeHi[g + 1]);
+    }
+    nodeLo[node] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+    nodeHi[node] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+    __threadfence();
+    node = parentOfInternal[node];
+  }
+}
+
+__device__ __forceinline__ uint32_t childRef(int first, int last, int internalIdx) {
+  uint32_t cnt = (uint32_t)(last - first + 1);
+  if (cnt <= VR_LEAF_MAX)
+    return VR_LEAF_FLAG | ((uint32_t)first << 4) | cnt;
+  return (uint32_t)internalIdx;
+}
+
+__global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
+                           const int2 *range, const int *split, const float4 *nodeLo,
+                           const float4 *nodeHi, Node2 *nodes, unsigned int *stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+  int2 r = range[i];
+  if ((uint32_t)(r.y - r.x + 1) <= VR_LEAF_MAX && i != 0)
+    return;  // inside a collapsed leaf (never referenced)
+  int g = split[i];
+  float4 l0, h0, l1, h1;
+  uint32_t ref0, ref1;
+  if (r.x == g) {
+    uint32_t p = sorted[g];
+    l0 = lo[p];
+    h0 = hi[p];
+    ref0 = VR_LEAF_FLAG | ((uint32_t)g << 4) | 1u;
+  } else {
+    l0 = nodeLo[g];
+    h0 = nodeHi[g];
+    int2 rc = range[g];
+    ref0 = childRef(rc.x, rc.y, g);
+  }
+  if (r.y == g + 1) {
+    uint32_t p = sorted[g + 1];
+    l1 = lo[p];
+    h1 = hi[p];
+    ref1 = VR_LEAF_FLAG | ((uint32_t)(g + 1) << 4) | 1u;
+  } else {
+    l1 = nodeLo[g + 1];
+    h1 = nodeHi[g + 1];
+    int2 rc = range[g + 1];
+    ref1 = childRef(rc.x, rc.y, g + 1);
+  }
+  Node2 nd;
+  nd.a = make_float4(l0.x, l0.y, l0.z, h0.x);
+  nd.b = make_float4(h0.y, h0.z, l1.x, l1.y);
+  nd.c = make_float4(l1.z, h1.x, h1.y, h1.z);
+  nd.d = make_float4(__uint_as_float(ref0), __uint_as_float(ref1), 0.f, 0.f);
+  nodes[i] = nd;
+  atomicAdd(&stats[0], 1u);
+  unsigned leaves = ((ref0 & VR_LEAF_FLAG) ? 1u : 0u) + ((ref1 & VR_LEAF_FLAG) ? 1u : 0u);
+  if (leaves)
+    atomicAdd(&stats[1], leaves);
+  if (ref0 & VR_LEAF_FLAG)
+    atomicMax(&stats[2], ref0 & 15u);
+  if (ref1 & VR_LEAF_FLAG)
+    atomicMax(&stats[2], ref1 & 15u);
+}
+
+}  // namespace
+
+#define VR_CK(x)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) {                                                                       \
+      cleanup();                                                                                   \
+      return e_;                                                                                   \
+    }                                                                                              \
+  } while (0)
+
+cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, const float sceneLo[3],
+                     const float sceneHi[3], cudaStream_t stream, Bvh *out) {
+  freeBvh(out);
+  unsigned long long *keys = nullptr, *keysSorted = nullptr;
+  uint32_t *vals = nullptr;
+  void *tmp = nullptr;
+  int2 *range = nullptr;
+  int *split = nullptr, *parI = nullptr, *parL = nullptr, *flags = nullptr;
+  float4 *nodeLo = nullptr, *nodeHi = nullptr;
+  unsigned int *stats = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(keys);
+    cudaFree(keysSorted);
+    cudaFree(vals);
+    cudaFree(tmp);
+    cudaFree(range);
+    cudaFree(split);
+    cudaFree(parI);
+    cudaFree(parL);
+    cudaFree(flags);
+    cudaFree(nodeLo);
+    cudaFree(nodeHi);
+    cudaFree(stats);
+    if (e0)
+      cudaEventDestroy(e0);
+    if (e1)
+      cudaEventDestroy(e1);
+  };
+  if (n == 0) {
+    out->rootRef = VR_INVALID_ID;
+    return cudaSuccess;
+  }
+  VR_CK(cudaEventCreate(&e0));
+  VR_CK(cudaEventCreate(&e1));
+  VR_CK(cudaEventRecord(e0, stream));
+  VR_CK(cudaMalloc(&keys, sizeof(unsigned long long) * n));
+  VR_CK(cudaMalloc(&keysSorted, sizeof(unsigned long long) * n));
+  VR_CK(cudaMalloc(&vals, sizeof(uint32_t) * n));
+  VR_CK(cudaMalloc(&out->sortedToOrig, sizeof(uint32_t) * n));
+  float3 sLo = make_float3(sceneLo[0], sceneLo[1], sceneLo[2]);
+  float3 sInv;
+  sInv.x = sceneHi[0] > sceneLo[0] ? 1.f / (sceneHi[0] - sceneLo[0]) : 0.f;
+  sInv.y = sceneHi[1] > sceneLo[1] ? 1.f / (sceneHi[1] - sceneLo[1]) : 0.f;
+  sInv.z = sceneHi[2] > sceneLo[2] ? 1.f / (sceneHi[2] - sceneLo[2]) : 0.f;
+  const int B = 256;
+  mortonKernel<<<(n + B - 1) / B, B, 0, stream>>>(primLo, primHi, n, sLo, sInv, keys, vals);
+  VR_CK(cudaGetLastError());
+  size_t tmpBytes = 0;
+  VR_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, vals,
+                                        out->sortedToOrig, (int)n, 0, 63, stream));
+  VR_CK(cudaMalloc(&tmp, tmpBytes ? tmpBytes : 16));
+  VR_CK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, out->sortedToOrig,
+                                        (int)n, 0, 63, stream));
+  if (n <= VR_LEAF_MAX) {
+    out->rootRef = VR_LEAF_FLAG | (0u << 4) | n;
+    out->numNodes = 0;
+    out->numLeaves = 1;
+    out->maxLeaf = n;
+    VR_CK(cudaMalloc(&out->nodes, sizeof(Node2)));
+  } else {
+    VR_CK(cudaMalloc(&range, sizeof(int2) * (n - 1)));
+    VR_CK(cudaMalloc(&split, sizeof(int) * (n - 1)));
+    VR_CK(cudaMalloc(&parI, sizeof(int) * (n - 1)));
+    VR_CK(cudaMalloc(&parL, sizeof(int) * n));
+    VR_CK(cudaMalloc(&flags, sizeof(int) * (n - 1)));
+    VR_CK(cudaMalloc(&nodeLo, sizeof(float4) * (n - 1)));
+    VR_CK(cudaMalloc(&nodeHi, sizeof(float4) * (n - 1)));
+    VR_CK(cudaMalloc(&stats, sizeof(unsigned int) * 4));
+    VR_CK(cudaMalloc(&out->nodes, sizeof(Node2) * (n - 1)));
+    VR_CK(cudaMemsetAsync(flags, 0, sizeof(int) * (n - 1), stream));
+    VR_CK(cudaMemsetAsync(stats, 0, sizeof(unsigned int) * 4, stream));
+    radixTreeKernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(keysSorted, (int)n, range, split, parI,
+                                                           parL);
+    VR_CK(cudaGetLastError());
+    refitKernel<<<(n + B - 1) / B, B, 0, stream>>>(primLo, primHi, out->sortedToOrig, (int)n,
+                                                   range, split, parI, parL, nodeLo, nodeHi, flags);
+    VR_CK(cudaGetLastError());
+    emitKernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(primLo, primHi, out->sortedToOrig, (int)n,
+                                                      range, split, nodeLo, nodeHi, out->nodes,
+                                                      stats);
+    VR_CK(cudaGetLastError());
+    unsigned int hs[4];
+    VR_CK(cudaMemcpyAsync(hs, stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
+    VR_CK(cudaStreamSynchronize(stream));
+    out->numNodes = hs[0];
+    out->numLeaves = hs[1];
+    out->maxLeaf = hs[2];
+    out->rootRef = 0u;
+  }
+  VR_CK(cudaEventRecord(e1, stream));
+  VR_CK(cudaEventSynchronize(e1));
+  cudaEventElapsedTime(&out->buildMs, e0, e1);
+  cleanup();
+  return cudaSuccess;
+}
+
+void freeBvh(Bvh *b) {
+  cudaFree(b->nodes);
+  cudaFree(b->sortedToOrig);
+  *b = Bvh();
+}
+
+}  // namespace vr
