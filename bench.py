@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the Monte Carlo flux hot path (BASELINE.json metric: rays/s on
+the synthetic 1M-disk trench, two particles: diffuse neutral + coned-cosine
+ion).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm
+
+One step = one pass of the hot path over one batch of rays: `--rays` rays per
+particle per GPU (default 2.5e8, so the default K=4 steps trace the config's
+1e9 rays per particle on one GPU).  Ray indices of consecutive steps and of
+different ranks are disjoint slices of one job, so weak scaling over N GPUs is
+the same Monte Carlo estimate with N times the rays.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 12345 + 1
+ION = dict(kind=2, sticking=0.5, power=100.0, cone=float(np.deg2rad(85.0)))
+NEUTRAL = dict(kind=0, sticking=0.1, power=1.0, cone=0.0)
+WORKLOAD = "C4 synthetic trench, 999,999 disks (gridDelta 1, periodic), diffuse neutral " \
+           "(sticking 0.1, cosine) + coned-cosine ion (sticking 0.5, power 100)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_rate(points, normals, gd, target_seconds, threads=None):
+    """rays/s of the reference's own TraceKernel (oracle/_ref: unmodified
+    reference headers + substitute intersector) -- or of the plain-C oracle
+    when oracle/_ref was not built -- over both particles.  Two runs of
+    different size; the rate is the slope, which removes the scene build that
+    the reference's timer includes (rtcJoinCommitScene inside the timed
+    region, rayTraceKernel.hpp:84-91)."""
+    from oracle import pyoracle as po
+    cores = os.cpu_count()
+    if po.have_ref():
+        kind = "reference"
+
+        def run(nrays):
+            tot = 0.0
+            for p in (NEUTRAL, ION):
+                _, _, sec = po.ref_trace_disk(3, points, normals, gd, [1, 1, 1], po.POS_Z,
+                                              p["kind"], p["sticking"], p["power"], p["cone"],
+                                              rays_fixed=nrays, seed=12345, threads=threads)
+                tot += sec
+            return tot
+    else:
+        kind = "port"
+        from viennaray_b200 import host
+        sc = po.OracleScene(3)
+        r = host.disk_radius(gd, 3)
+        sc.set_disks(points, normals, r)
+        sc.setup(po.POS_Z, [1, 1, 1], r)
+
+        def run(nrays):
+            t = time.perf_counter()
+            for k, p in enumerate((NEUTRAL, ION)):
+                sc.trace(po.Particle(p["kind"], p["sticking"], p["power"], p["cone"]),
+                         sc.config(nrays, SEED, stream=k))
+            return time.perf_counter() - t
+    n1 = 200_000
+    t1 = run(n1)
+    t2 = run(2 * n1)
+    rate = 2 * n1 / max(t2 - t1, 1e-9)  # rays/s over both particles (2 particles x n1 more rays)
+    n3 = int(min(max(rate * target_seconds / 2, 4 * n1), 5e7))
+    t3 = run(n3)
+    rate = 2 * (n3 - n1) / max(t3 - t1, 1e-9)
+    sample = "%d + %d rays per particle (slope of two runs), %d host threads" % (n1, n3, cores)
+    return rate, kind, cores, sample, n3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=float, default=2.5e8, help="rays per particle per GPU per step")
+    ap.add_argument("--warmup-rays", type=float, default=2e7)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slices", type=int, default=999, help="trench length (999 = the 1M config)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from viennaray_b200 import scenes
+    points, normals, gd = scenes.trench(num_slices=args.slices)
+    n = len(points)
+    config = {"workload": WORKLOAD if args.slices == 999 else WORKLOAD + " [%d slices]" % args.slices,
+              "disks": n, "particles": 2, "rays_per_particle_per_gpu_per_step": int(args.rays),
+              "seed": SEED, "parallelism": "ray-sharded x%d, scene replicated" % world,
+              "l2": "L2 flushed between steps (256 MiB write)"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        per_step = []
+        kind = cores = sample = None
+        for k in range(args.warmup + args.steps):
+            if k < args.warmup and k > 0:
+                continue  # one warm-up pass is enough for a CPU loop
+            t = time.perf_counter()
+            rate, kind, cores, sample, _ = cpu_reference_rate(
+                points, normals, gd, max(args.cpu_seconds / max(args.steps, 1), 3.0))
+            if k >= args.warmup:
+                per_step.append((rate, time.perf_counter() - t))
+        value = float(np.mean([r for r, _ in per_step]))
+        line = {"impl": "reference", "metric": "rays/s", "value": value, "unit": "rays/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * float(np.mean([t for _, t in per_step])),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": kind,
+                                 "sample": sample + "; reference TraceKernel + substitute "
+                                 "intersector (Embree absent)" if kind == "reference" else sample},
+                "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ CUDA arm
+    import torch
+    import torch.distributed as dist
+    from viennaray_b200 import capi, host
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    D = 3
+    r = host.disk_radius(gd, D)
+    xyzr = np.concatenate([points, np.full((n, 1), r, np.float32)], 1)
+    t0 = time.perf_counter()
+    nb_off, nb_idx = capi.build_neighbors(D, points, np.float32(2) * r)
+    t_nb = time.perf_counter() - t0
+    glo, ghi = host.geometry_bbox(points, D)
+    lo, hi = host.adjust_bbox(glo, ghi, host.POS_Z, r, D)
+    _, first, second, _, _ = host.trace_settings(host.POS_Z)
+    src = host.source_desc(lo, hi, host.POS_Z)
+    parts = [capi.ParticleDesc(p["kind"], p["sticking"], p["power"], p["cone"])
+             for p in (NEUTRAL, ION)]
+
+    ctx = capi.Context(local_rank)
+
+    def upload_and_commit():
+        ctx.set_disks(xyzr, normals, nb_off, nb_idx)
+        ctx.set_boundary(lo, hi, first, second, 1, 1, D)
+        ctx.commit()
+
+    upload_and_commit()
+    bvh = ctx.bvh_stats()
+    rays = int(args.rays)
+    total_rays_job = rays * world * (args.steps + args.warmup + 2)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def shard(step, count):
+        begin = (step * world + rank) * rays
+        return host.config(total_rays_job, SEED, begin, begin + count)
+
+    def all_reduce_flux():
+        if world == 1:
+            return
+        ptr, words = ctx.flux_device()
+        iface = {"shape": (words,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        holder = type("Buf", (), {"__cuda_array_interface__": iface})()
+        t = torch.as_tensor(holder, device="cuda")
+        with torch.cuda.stream(stream):
+            dist.all_reduce(t)
+
+    # per-ray work of this workload (same kernel; counters ride in registers)
+    os.environ["VR_COUNT_WORK"] = "1"
+    cctx = capi.Context(local_rank)
+    cctx.set_disks(xyzr, normals, nb_off, nb_idx)
+    cctx.set_boundary(lo, hi, first, second, 1, 1, D)
+    cctx.commit()
+    os.environ.pop("VR_COUNT_WORK")
+    count_rays = 4_000_000
+    cctx.trace_device(src, parts, host.config(count_rays, SEED), sync=True)
+    work = cctx.work_counters()
+    _, cinfo = cctx.flux_download()
+    cctx.close()
+    node_b, prim_b = bvh["node_bytes"], 32
+    bytes_per_ray = (work["node_visits"] * node_b + work["prim_tests"] * prim_b +
+                     work["nb_tests"] * (4 + 32) + work["flux_adds"] * 8) / (2.0 * count_rays)
+
+    # warm-up
+    for k in range(args.warmup):
+        ctx.trace_device(src, parts, shard(k, int(args.warmup_rays)))
+        all_reduce_flux()
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    kernel_ms = 0.0
+    ev0.record(stream)
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        ctx.trace_device(src, parts, shard(args.warmup + k, rays))
+        all_reduce_flux()
+        if world > 1:
+            ctx.synchronize()
+        kernel_ms += 0.0
+    ev1.record(stream)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.stop.set()
+    sampler.join()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    last_kernel_ms = ctx.last_kernel_ms()  # trace kernels of the last step (both particles)
+    _ = ctx.flux_download()
+    last_kernel_ms = ctx.last_kernel_ms()
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    rays_total = 2.0 * rays * world * args.steps
+    value = rays_total / (elapsed_ms * 1e-3)
+
+    # end-to-end through the host C ABI: upload scene, build BVH, trace, read flux
+    e2e_rays = rays
+    t_e2e = []
+    for k in range(max(1, min(args.steps, 2))):
+        t = time.perf_counter()
+        upload_and_commit()
+        flux, infos = ctx.trace(src, parts, shard(args.warmup + args.steps + k, e2e_rays))
+        t_e2e.append(time.perf_counter() - t)
+    if world > 1:
+        t = torch.tensor([max(t_e2e)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    else:
+        e2e_s = float(np.mean(t_e2e))
+    e2e_value = 2.0 * e2e_rays * world / e2e_s
+    h2d = xyzr.nbytes + normals.nbytes + nb_off.nbytes + nb_idx.nbytes
+    d2h = flux.nbytes + 2 * 72
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    kernel_rate = 2.0 * rays / (last_kernel_ms * 1e-3)  # rays/s inside the trace kernels
+    achieved = kernel_rate * bytes_per_ray / 1e9
+    line = {
+        "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h),
+                "what": "vr_scene_set_disks + vr_scene_commit (device BVH build) + vr_trace with "
+                        "host buffers"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_ray": bytes_per_ray,
+                     "per_ray": {k: v / (2.0 * count_rays) for k, v in work.items()},
+                     "kernel_ms_per_step": last_kernel_ms,
+                     "note": "algorithmic bytes = counted node visits x %d B + primitive tests x "
+                             "32 B + neighbour tests x 36 B + flux adds x 8 B" % node_b},
+        "clocks": sampler.summary(),
+        "bvh": bvh, "neighbor_build_host_s": t_nb,
+        "walk": {"traces_per_ray": [i.totalRaysTraced / count_rays for i in cinfo],
+                 "geo_hits_per_ray": [i.geometryHits / count_rays for i in cinfo]},
+    }
+    if not args.no_cpu_baseline:
+        rate, kind, cores, sample, _ = cpu_reference_rate(points, normals, gd, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": kind,
+                                "sample": sample}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
