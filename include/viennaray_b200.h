@@ -134,6 +134,8 @@ void *vr_ctx_stream(vr_ctx *ctx);
 int vr_ctx_synchronize(vr_ctx *ctx);
 /* device time in ms of the trace kernels of the last vr_trace* call */
 float vr_last_kernel_ms(vr_ctx *ctx);
+/* kernels launched / wavefront iterations run by the last vr_trace* call */
+int vr_last_launch_count(vr_ctx *ctx, int *kernelsOut, int *iterationsOut);
 
 /* ---- host-side geometry helpers (C++ inside the library) ---------------- */
 /* Neighbour sets of PointNeighborhood::init (rayPointNeighborhood.hpp:43-107,

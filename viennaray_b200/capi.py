@@ -19,7 +19,7 @@ EXPORTS = [
     "vr_ctx_create", "vr_ctx_destroy", "vr_last_error", "vr_scene_set_disks",
     "vr_scene_set_triangles", "vr_scene_set_boundary", "vr_scene_commit", "vr_trace",
     "vr_trace_device", "vr_flux_device", "vr_flux_download", "vr_flux_download_fixed",
-    "vr_ctx_stream", "vr_ctx_synchronize", "vr_last_kernel_ms", "vr_build_neighbors", "vr_free",
+    "vr_ctx_stream", "vr_ctx_synchronize", "vr_last_kernel_ms", "vr_last_launch_count", "vr_build_neighbors", "vr_free",
     "vr_debug_intersect", "vr_debug_source_rays", "vr_debug_math", "vr_debug_philox",
     "vr_debug_reflect", "vr_debug_bvh_stats", "vr_debug_work_counters",
 ]
@@ -89,6 +89,7 @@ def lib():
         L.vr_ctx_synchronize.argtypes = [_vp]
         L.vr_last_kernel_ms.restype = C.c_float
         L.vr_last_kernel_ms.argtypes = [_vp]
+        L.vr_last_launch_count.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.vr_build_neighbors.argtypes = [C.c_int, _vp, C.c_uint32, C.c_float, C.POINTER(_vp),
                                          C.POINTER(_vp)]
         L.vr_free.restype = None
@@ -235,6 +236,11 @@ class Context:
 
     def last_kernel_ms(self):
         return float(self.L.vr_last_kernel_ms(self.h))
+
+    def last_launch_count(self):
+        k, it = C.c_int(), C.c_int()
+        self._ck(self.L.vr_last_launch_count(self.h, C.byref(k), C.byref(it)))
+        return k.value, it.value
 
     def debug_intersect(self, rays, nb_cap=16):
         rays = np.ascontiguousarray(rays, np.float32)

@@ -40,14 +40,21 @@ struct vr_ctx {
   // results of the last trace
   unsigned long long *dResult = nullptr;  // np*n flux words + np*8 counters
   unsigned long long *dFluxOrig = nullptr;
-  unsigned long long *dCursor = nullptr;
+  unsigned long long *dCursor = nullptr;   // [0] ray cursor
+  unsigned int *dSlotCursor = nullptr;      // [0] slot cursor, [1] live count
+  unsigned long long *dCounterCopies = nullptr;  // VR_COUNTER_COPIES x 8
+  unsigned int *hLive = nullptr;            // pinned ring of live counts
+  cudaEvent_t liveEv[4] = {nullptr, nullptr, nullptr, nullptr};
+  RayPool pool{};
   unsigned long long *dWork = nullptr;
   size_t resultWords = 0;
   int numParticles = 0;
   uint64_t lastNumRays = 0;
   float lastMs = 0.f;
   int kernelLaunches = 0;
+  int iterations = 0;
   bool countWork = false;
+  uint32_t poolSlots = 1u << 22;
 };
 
 static std::string g_createError;
@@ -89,6 +96,46 @@ static void freeResults(vr_ctx *c) {
   c->numParticles = 0;
 }
 
+static void freePool(vr_ctx *c) {
+  cudaFree(c->pool.od0);
+  cudaFree(c->pool.od1);
+  cudaFree(c->pool.hit);
+  cudaFree(c->pool.rng);
+  cudaFree(c->pool.meta);
+  cudaFree(c->pool.weight);
+  cudaFree(c->pool.dir3);
+  c->pool = RayPool{};
+}
+
+static cudaError_t ensurePool(vr_ctx *c, uint32_t slots) {
+  if (c->pool.capacity >= slots && c->pool.od0)
+    return cudaSuccess;
+  freePool(c);
+  cudaError_t e;
+  if ((e = cudaMalloc(&c->pool.od0, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&c->pool.od1, sizeof(float2) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&c->pool.hit, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&c->pool.rng, sizeof(uint4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&c->pool.meta, sizeof(uint4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&c->pool.weight, sizeof(float) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&c->pool.dir3, sizeof(float4) * (size_t)slots)) != cudaSuccess) {
+    freePool(c);
+    return e;
+  }
+  c->pool.capacity = slots;
+  return cudaSuccess;
+}
+
+__global__ void reduceCountersKernel(const unsigned long long *copies, unsigned long long *out) {
+  const int k = threadIdx.x;
+  if (k < 8) {
+    unsigned long long v = 0;
+    for (int c = 0; c < VR_COUNTER_COPIES; ++c)
+      v += copies[c * 8 + k];
+    out[k] = v;
+  }
+}
+
 extern "C" {
 
 const char *vr_last_error(const vr_ctx *ctx) {
@@ -123,10 +170,23 @@ int vr_ctx_create(int cudaDevice, vr_ctx **out) {
   ctx->numSMs = prop.multiProcessorCount;
   const char *cw = getenv("VR_COUNT_WORK");
   ctx->countWork = cw && cw[0] == '1';
+  if (const char *ps = getenv("VR_POOL_SLOTS")) {
+    long v = atol(ps);
+    if (v >= 1024 && v <= (1l << 26))
+      ctx->poolSlots = (uint32_t)v;
+  }
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->dCursor, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->dSlotCursor, 2 * sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->dCounterCopies,
+                      VR_COUNTER_COPIES * 8 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMallocHost(&ctx->hLive, 4 * sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->liveEv[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->liveEv[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->liveEv[2], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->liveEv[3], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->dWork, 4 * sizeof(unsigned long long))) != cudaSuccess) {
     failCuda(nullptr, e, "vr_ctx_create");
     vr_ctx_destroy(ctx);
@@ -143,6 +203,13 @@ void vr_ctx_destroy(vr_ctx *ctx) {
   freeDeviceScene(ctx);
   freeResults(ctx);
   cudaFree(ctx->dCursor);
+  cudaFree(ctx->dSlotCursor);
+  cudaFree(ctx->dCounterCopies);
+  cudaFreeHost(ctx->hLive);
+  for (auto &e : ctx->liveEv)
+    if (e)
+      cudaEventDestroy(e);
+  freePool(ctx);
   cudaFree(ctx->dWork);
   if (ctx->ev0)
     cudaEventDestroy(ctx->ev0);
@@ -162,6 +229,15 @@ int vr_ctx_synchronize(vr_ctx *ctx) {
   return VR_OK;
 }
 float vr_last_kernel_ms(vr_ctx *ctx) { return ctx ? ctx->lastMs : 0.f; }
+int vr_last_launch_count(vr_ctx *ctx, int *kernelsOut, int *iterationsOut) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  if (kernelsOut)
+    *kernelsOut = ctx->kernelLaunches;
+  if (iterationsOut)
+    *iterationsOut = ctx->iterations;
+  return VR_OK;
+}
 
 int vr_scene_set_disks(vr_ctx *ctx, const float *xyzr, const float *nxyz, uint32_t n,
                        const int32_t *materialIds, const uint32_t *nbOffsets,
@@ -434,7 +510,11 @@ static int fillParams(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_
   p.stream = (uint32_t)particleIndex;
   p.maxReflections = cfg->maxReflections;
   p.maxBoundaryHits = cfg->maxBoundaryHits;
+  p.pool = ctx->pool;
+  p.numSlots = 0;
   p.rayCursor = ctx->dCursor;
+  p.slotCursor = ctx->dSlotCursor;
+  p.liveCount = ctx->dSlotCursor + 1;
   p.work = ctx->countWork ? ctx->dWork : nullptr;
   return VR_OK;
 }
@@ -462,6 +542,10 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
   if (ctx->countWork)
     CK(cudaMemsetAsync(ctx->dWork, 0, 4 * sizeof(unsigned long long), ctx->stream));
   ctx->kernelLaunches = 0;
+  ctx->iterations = 0;
+  const uint64_t shardRays = cfg ? cfg->rayIdxEnd - cfg->rayIdxBegin : 0;
+  const uint32_t slots = (uint32_t)std::min<uint64_t>(ctx->poolSlots, std::max<uint64_t>(shardRays, 1));
+  CK(ensurePool(ctx, slots));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int k = 0; k < np; ++k) {
     TraceParams p;
@@ -469,10 +553,37 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
     if (rc)
       return rc;
     p.flux = ctx->dResult + (size_t)k * n;
-    p.counters = ctx->dResult + (size_t)np * n + (size_t)k * 8;
+    p.counters = ctx->dCounterCopies;
+    p.numSlots = slots;
+    if (p.idxEnd == p.idxBegin)
+      continue;
     CK(cudaMemsetAsync(ctx->dCursor, 0, sizeof(unsigned long long), ctx->stream));
-    if (p.idxEnd > p.idxBegin)
-      CK(launchTrace(p, ctx->numSMs, ctx->stream, &ctx->kernelLaunches));
+    CK(cudaMemsetAsync(ctx->dSlotCursor, 0, 2 * sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->dCounterCopies, 0, VR_COUNTER_COPIES * 8 * sizeof(unsigned long long),
+                       ctx->stream));
+    CK(launchInitPool(p, ctx->stream));
+    ++ctx->kernelLaunches;
+    // wavefront iterations; the live count of iteration i is read back two
+    // iterations later so the device never waits for the host
+    for (int it = 0;; ++it) {
+      CK(launchTraverse(p, ctx->numSMs, ctx->stream));
+      CK(launchShade(p, ctx->stream));
+      ctx->kernelLaunches += 2;
+      ++ctx->iterations;
+      const int r = it & 3;
+      CK(cudaMemcpyAsync(&ctx->hLive[r], p.liveCount, sizeof(unsigned int),
+                         cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaEventRecord(ctx->liveEv[r], ctx->stream));
+      if (it >= 2) {
+        const int q = (it - 2) & 3;
+        CK(cudaEventSynchronize(ctx->liveEv[q]));
+        if (ctx->hLive[q] == 0u)
+          break;
+      }
+    }
+    reduceCountersKernel<<<1, 32, 0, ctx->stream>>>(ctx->dCounterCopies,
+                                                    ctx->dResult + (size_t)np * n + (size_t)k * 8);
+    CK(cudaGetLastError());
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (sync) {
@@ -666,8 +777,21 @@ int vr_debug_intersect(vr_ctx *ctx, const float *rays, uint32_t m, uint32_t *geo
   }
   CKD(cudaMemcpyAsync(dRays, rays, sizeof(float) * 6 * (size_t)m, cudaMemcpyHostToDevice,
                       ctx->stream));
-  CKD(launchDebugIntersect(ctx->scene, dRays, m, dGeom, dPrim, dT, nbCap, dCnt, dNb,
-                           ctx->bvh.sortedToOrig, ctx->stream));
+  CKD(ensurePool(ctx, std::max<uint32_t>(m, 1u)));
+  {
+    TraceParams p{};
+    p.scene = ctx->scene;
+    p.pool = ctx->pool;
+    p.numSlots = m;
+    p.slotCursor = ctx->dSlotCursor;
+    p.liveCount = ctx->dSlotCursor + 1;
+    p.work = nullptr;
+    CKD(cudaMemsetAsync(ctx->dSlotCursor, 0, 2 * sizeof(unsigned int), ctx->stream));
+    CKD(launchDebugLoadRays(ctx->pool, dRays, m, ctx->stream));
+    CKD(launchTraverse(p, ctx->numSMs, ctx->stream));
+    CKD(launchDebugReadHits(ctx->scene, ctx->pool, m, dGeom, dPrim, dT, wantNb ? nbCap : 0u,
+                            wantNb ? dCnt : nullptr, dNb, ctx->bvh.sortedToOrig, ctx->stream));
+  }
   CKD(cudaMemcpyAsync(geomOut, dGeom, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
   CKD(cudaMemcpyAsync(primOut, dPrim, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
   CKD(cudaMemcpyAsync(tOut, dT, sizeof(float) * m, cudaMemcpyDeviceToHost, ctx->stream));

@@ -79,6 +79,22 @@ struct Rng {
     blk = 0;
     left = 0;
   }
+  // state that survives between kernels: at most three buffered words
+  __device__ __forceinline__ uint4 save() const {
+    return make_uint4(b0, b1, b2, blk | ((uint32_t)left << 30));
+  }
+  __device__ __forceinline__ void load(uint4 s, uint32_t seed, uint32_t stream, uint64_t idx) {
+    k0 = seed;
+    k1 = stream;
+    c0 = (uint32_t)idx;
+    c1 = (uint32_t)(idx >> 32);
+    b0 = s.x;
+    b1 = s.y;
+    b2 = s.z;
+    b3 = 0u;
+    blk = s.w & 0x3fffffffu;
+    left = (int)(s.w >> 30);
+  }
   __device__ __forceinline__ uint32_t u32() {
     if (left == 0) {
       uint32_t o[4];

@@ -10,6 +10,7 @@
 #define VR_LEAF_MAX 4u            // primitives per BVH leaf
 #define VR_LEAF_FLAG 0x80000000u  // child reference: leaf(first << 4 | count)
 #define VR_FIXED_SCALE 1073741824.0f
+#define VR_COUNTER_COPIES 16      // replicated TraceInfo counters (summed on download)
 
 namespace vr {
 
@@ -25,7 +26,7 @@ struct DeviceScene {
   int geoType;  // 0 disk, 1 triangle
   uint32_t numPrims;
   // primitives in BVH (Morton) order -- the INTERNAL primitive index
-  const float4 *primA;  // disk: x,y,z,r        triangle: v0
+  const float4 *primA;  // disk: x,y,z,r        triangle: v0 (w = original ID)
   const float4 *primB;  // disk: nx,ny,nz,orig  triangle: v1
   const float4 *primC;  //                      triangle: v2
   const float4 *primN;  // disk: = primB        triangle: nx,ny,nz,orig
@@ -40,17 +41,35 @@ struct DeviceScene {
   float btri[8][3][3];  // 8 triangles x 3 vertices
 };
 
+// Resident pool of rays in flight (structure of arrays, one slot per ray).
+// The traverse kernel reads od0/od1 and writes hit; the shade kernel owns the
+// rest.  A slot with dir.x = NaN is empty.
+struct RayPool {
+  uint32_t capacity;
+  float4 *od0;   // org.x, org.y, org.z, dir.x
+  float2 *od1;   // dir.y, dir.z
+  float4 *hit;   // t, prim (bits), geom (bits), -
+  uint4 *rng;    // b0, b1, b2, blk | left << 30
+  uint4 *meta;   // idx lo, idx hi, numReflections, boundaryHits | hitFromBack << 31
+  float *weight;
+  float4 *dir3;  // particle-facing direction (differs from the ray's in 2D only)
+};
+
 struct TraceParams {
   DeviceScene scene;
+  RayPool pool;
   vr_source_desc src;
   vr_particle_desc particle;
   float ee;  // 1 / (sourcePower + 1), raySourceRandom.hpp:21
   uint64_t idxBegin, idxEnd;
   uint32_t seed, stream;
   uint32_t maxReflections, maxBoundaryHits;
+  uint32_t numSlots;             // slots in use this launch (<= pool.capacity)
   unsigned long long *flux;      // numPrims fixed-point sums (internal order)
-  unsigned long long *counters;  // 8 TraceInfo counters
-  unsigned long long *rayCursor; // next ray offset
+  unsigned long long *counters;  // VR_COUNTER_COPIES x 8 TraceInfo counters
+  unsigned long long *rayCursor; // rays handed out so far
+  unsigned int *slotCursor;      // traverse kernel: next slot
+  unsigned int *liveCount;       // shade kernel: slots still alive afterwards
   unsigned long long *work;      // optional work counters (4) or null
 };
 
@@ -63,8 +82,6 @@ struct Bvh {
   float buildMs = 0.f;
   uint32_t numLeaves = 0, maxLeaf = 0;
 };
-// primLo/primHi: device float4 arrays of per-primitive padded boxes (original
-// order); centers from the box centre.  sceneLo/Hi: host.
 cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, const float sceneLo[3],
                      const float sceneHi[3], cudaStream_t stream, Bvh *out);
 void freeBvh(Bvh *b);
@@ -74,11 +91,16 @@ cudaError_t launchDiskBounds(const float4 *xyzr, const float4 *nrm, uint32_t n, 
                              float4 *hi, cudaStream_t s);
 cudaError_t launchTriBounds(const float4 *v0, const float4 *v1, const float4 *v2, uint32_t n,
                             float4 *lo, float4 *hi, cudaStream_t s);
-cudaError_t launchTrace(const TraceParams &p, int numSMs, cudaStream_t s, int *launches);
-cudaError_t launchDebugIntersect(const DeviceScene &sc, const float *rays, uint32_t m,
-                                 uint32_t *geom, uint32_t *prim, float *t, uint32_t nbCap,
-                                 uint32_t *nbCount, uint32_t *nbOut, const uint32_t *sortedToOrig,
-                                 cudaStream_t s);
+// one wavefront iteration = traverse + shade; init fills the pool
+cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s);
+cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s);
+cudaError_t launchShade(const TraceParams &p, cudaStream_t s);
+cudaError_t launchDebugLoadRays(const RayPool &pool, const float *rays, uint32_t m,
+                                cudaStream_t s);
+cudaError_t launchDebugReadHits(const DeviceScene &sc, const RayPool &pool, uint32_t m,
+                                uint32_t *geom, uint32_t *prim, float *t, uint32_t nbCap,
+                                uint32_t *nbCount, uint32_t *nbOut, const uint32_t *sortedToOrig,
+                                cudaStream_t s);
 cudaError_t launchDebugSourceRays(const TraceParams &p, uint64_t idxBegin, uint32_t m, float *rays,
                                   cudaStream_t s);
 cudaError_t launchDebugMath(int which, const float *x, uint32_t m, float param, float *out,

@@ -1,99 +1,229 @@
-// The hot path: a persistent kernel that runs the whole Monte Carlo walk of
-// rayInternal::TraceKernel::apply (rayTraceKernel.hpp:117-338) per ray --
-// source sampling, BVH traversal with disk / triangle tests, boundary
-// handling, neighbour spread, particle reflection and Russian roulette -- and
-// regenerates finished lanes from a global ray cursor.
+// The hot path as a wavefront over a resident ray pool:
+//
+//   traverseKernel  persistent warps; every lane owns one ray at a time and
+//                   replaces it from the slot cursor as soon as it finishes
+//                   (warp-level compaction of the work), while-while traversal
+//                   of the BVH with disk / triangle tests; boundary box first
+//                   so its hit bounds the traversal.  Writes one hit per slot.
+//   shadeKernel     one thread per slot: boundary handling, backface rule,
+//                   neighbour spread, flux accumulation, particle reflection,
+//                   Russian roulette (rayTraceKernel.hpp:172-333) and in-place
+//                   regeneration of finished rays from the source
+//                   (rayTraceKernel.hpp:120-143).
+//
+// The host alternates the two until no slot is alive.  Results are identical
+// to running each ray to completion on its own (per-ray counter RNG, fixed
+// point flux sums), which is what the CPU oracle does.
 #include "vr_device.cuh"
 
 namespace vr {
 
-// ---------------------------------------------------------------------------
-// closest hit over geometry (BVH) and the 8 boundary triangles
-// ---------------------------------------------------------------------------
 #define VR_STACK 96
+#define VR_DONE 0x7fffffffu  // traversal finished (not a valid node index)
 
-template <int GEO>
-__device__ __forceinline__ void testLeaf(const DeviceScene &sc, uint32_t ref, const V3 &org,
-                                         const V3 &dir, Hit &best, unsigned &primTests) {
-  uint32_t first = (ref & 0x7fffffffu) >> 4, count = ref & 15u;
-  for (uint32_t k = 0; k < count; ++k) {
-    uint32_t i = first + k;
-    if (GEO == 0) {
-      float4 P = __ldg(&sc.primA[i]);
-      float4 N = __ldg(&sc.primB[i]);
-      testDisk(P, N, i, org, dir, best);
-    } else {
-      float4 a = __ldg(&sc.primA[i]), b = __ldg(&sc.primB[i]), c = __ldg(&sc.primC[i]);
-      testTri({a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, 1u, i, __float_as_uint(a.w), org,
-              dir, best, nullptr);
+__device__ __forceinline__ bool slotEmpty(const float4 &od0) { return od0.w != od0.w; }
+
+// ---------------------------------------------------------------------------
+// boundary box (geomID 0).  The planes are axis aligned, so a cheap plane
+// distance selects the candidate triangles; the decision and the reported t
+// come from the exact triangle test.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void boundaryTest(const DeviceScene &sc, const V3 &org, const V3 &dir,
+                                             Hit &best) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int axis = k < 2 ? sc.firstDir : sc.secondDir;
+    const float c = sc.bbox[k & 1][axis];
+    const float da = comp(dir, axis);
+    if (da == 0.f)
+      continue;
+    const float tp = (c - comp(org, axis)) / da;
+    if (!(tp >= 0.5f * VR_TNEAR && tp <= best.t * 1.00001f + 1e-5f))
+      continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int i = 2 * k + j;
+      V3 v0 = {sc.btri[i][0][0], sc.btri[i][0][1], sc.btri[i][0][2]};
+      V3 v1 = {sc.btri[i][1][0], sc.btri[i][1][1], sc.btri[i][1][2]};
+      V3 v2 = {sc.btri[i][2][0], sc.btri[i][2][1], sc.btri[i][2][2]};
+      testTri(v0, v1, v2, 0u, (uint32_t)i, (uint32_t)i, org, dir, best, nullptr);
     }
-    ++primTests;
   }
 }
 
-template <int GEO>
-__device__ __forceinline__ void intersectScene(const DeviceScene &sc, const V3 &org, const V3 &dir,
-                                               Hit &best, V3 &bng, unsigned &nodeVisits,
-                                               unsigned &primTests) {
-  best.t = 3.402823466e+38f;
-  best.geom = VR_INVALID_ID;
-  best.prim = VR_INVALID_ID;
-  best.orig = VR_INVALID_ID;
-  const float idx = 1.f / dir.x, idy = 1.f / dir.y, idz = 1.f / dir.z;
+__device__ __forceinline__ unsigned long long warpSum(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
 
+// ---------------------------------------------------------------------------
+// traverse: closest hit of every live slot
+// ---------------------------------------------------------------------------
+template <int GEO>
+__global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__ TraceParams p) {
+  const DeviceScene &sc = p.scene;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned ltMask = (1u << lane) - 1u;
+  const uint32_t numSlots = p.numSlots;
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    *p.liveCount = 0u;  // the shade kernel that follows counts survivors
+
+  uint32_t slot = VR_INVALID_ID;
+  V3 org = {0.f, 0.f, 0.f}, dir = {0.f, 0.f, 1.f};
+  float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+  Hit best;
+  best.t = 0.f;
+  best.geom = best.prim = best.orig = VR_INVALID_ID;
+  uint32_t cur = VR_DONE;
   uint32_t stack[VR_STACK];
   int sp = 0;
-  uint32_t cur = sc.rootRef;
-  if (sc.numPrims == 0)
-    cur = VR_INVALID_ID;
-  while (cur != VR_INVALID_ID) {
-    if (cur & VR_LEAF_FLAG) {
-      testLeaf<GEO>(sc, cur, org, dir, best, primTests);
-      cur = sp ? stack[--sp] : VR_INVALID_ID;
+  bool exhausted = false;
+  unsigned wNodes = 0, wPrims = 0;
+
+  for (;;) {
+    // ---- replace finished lanes from the slot cursor ------------------------
+    const unsigned need = __ballot_sync(0xffffffffu, slot == VR_INVALID_ID);
+    if (need && !exhausted) {
+      const unsigned nNeed = __popc(need);
+      const int leader = __ffs(need) - 1;
+      unsigned base = 0;
+      if ((int)lane == leader)
+        base = atomicAdd(p.slotCursor, nNeed);
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (base + nNeed >= numSlots)
+        exhausted = true;
+      if (slot == VR_INVALID_ID) {
+        const unsigned s = base + __popc(need & ltMask);
+        if (s < numSlots) {
+          const float4 a = __ldcs(&p.pool.od0[s]);
+          if (!slotEmpty(a)) {
+            const float2 b = __ldcs(&p.pool.od1[s]);
+            slot = s;
+            org = {a.x, a.y, a.z};
+            dir = {a.w, b.x, b.y};
+            ix = 1.f / dir.x;
+            iy = 1.f / dir.y;
+            iz = 1.f / dir.z;
+            ox = -org.x * ix;
+            oy = -org.y * iy;
+            oz = -org.z * iz;
+            best.t = 3.402823466e+38f;
+            best.geom = best.prim = best.orig = VR_INVALID_ID;
+            boundaryTest(sc, org, dir, best);
+            sp = 0;
+            cur = sc.numPrims ? sc.rootRef : VR_DONE;
+          }
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, slot != VR_INVALID_ID)) {
+      if (exhausted)
+        break;
       continue;
     }
-    const Node2 *n = sc.nodes + cur;
-    const float4 a = __ldg(&n->a), b = __ldg(&n->b), c = __ldg(&n->c), d = __ldg(&n->d);
-    ++nodeVisits;
-    // conservative slab tests against [tnear, best.t]; NaN (0 * inf) compares
-    // false in fminf/fmaxf and leaves the other bound in place
-    float t0x = (a.x - org.x) * idx, t1x = (a.w - org.x) * idx;
-    float t0y = (a.y - org.y) * idy, t1y = (b.x - org.y) * idy;
-    float t0z = (a.z - org.z) * idz, t1z = (b.y - org.z) * idz;
-    float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
-    float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
-    float u0x = (b.z - org.x) * idx, u1x = (c.y - org.x) * idx;
-    float u0y = (b.w - org.y) * idy, u1y = (c.z - org.y) * idy;
-    float u0z = (c.x - org.z) * idz, u1z = (c.w - org.z) * idz;
-    float n1 = fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), VR_TNEAR));
-    float f1 = fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), best.t));
-    // widen: boxes are padded at build time; the factors absorb the rounding
-    // of the slab arithmetic itself
-    bool h0 = n0 * 0.999999f <= f0 * 1.000001f + 1e-6f;
-    bool h1 = n1 * 0.999999f <= f1 * 1.000001f + 1e-6f;
-    uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
-    if (h0 && h1) {
-      bool swap = n1 < n0;
-      uint32_t nearRef = swap ? r1 : r0, farRef = swap ? r0 : r1;
-      if (sp < VR_STACK)
-        stack[sp++] = farRef;
-      cur = nearRef;
-    } else if (h0) {
-      cur = r0;
-    } else if (h1) {
-      cur = r1;
-    } else {
-      cur = sp ? stack[--sp] : VR_INVALID_ID;
+
+    // ---- inner nodes ----------------------------------------------------------
+    while (cur < VR_DONE) {  // neither leaf (bit 31) nor DONE
+      const Node2 *n = sc.nodes + cur;
+      const float4 a = __ldg(&n->a), b = __ldg(&n->b), c = __ldg(&n->c), d = __ldg(&n->d);
+      ++wNodes;
+      // slab test t = lo * (1/d) - org/d with an explicit FMA; boxes were
+      // padded at build time and the comparison is widened, so rounding here
+      // can only add visits.  NaN (0 * inf) drops out of fminf / fmaxf.
+      const float t0x = __fmaf_rn(a.x, ix, ox), t1x = __fmaf_rn(a.w, ix, ox);
+      const float t0y = __fmaf_rn(a.y, iy, oy), t1y = __fmaf_rn(b.x, iy, oy);
+      const float t0z = __fmaf_rn(a.z, iz, oz), t1z = __fmaf_rn(b.y, iz, oz);
+      const float n0 =
+          fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
+      const float f0 =
+          fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
+      const float u0x = __fmaf_rn(b.z, ix, ox), u1x = __fmaf_rn(c.y, ix, ox);
+      const float u0y = __fmaf_rn(b.w, iy, oy), u1y = __fmaf_rn(c.z, iy, oy);
+      const float u0z = __fmaf_rn(c.x, iz, oz), u1z = __fmaf_rn(c.w, iz, oz);
+      const float n1 =
+          fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), VR_TNEAR));
+      const float f1 =
+          fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), best.t));
+      const bool h0 = n0 * 0.99999f <= f0 * 1.00001f + 1e-6f;
+      const bool h1 = n1 * 0.99999f <= f1 * 1.00001f + 1e-6f;
+      const uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
+      if (h0 && h1) {
+        const bool swap = n1 < n0;
+        if (sp < VR_STACK)
+          stack[sp++] = swap ? r0 : r1;
+        cur = swap ? r1 : r0;
+      } else if (h0) {
+        cur = r0;
+      } else if (h1) {
+        cur = r1;
+      } else {
+        cur = sp ? stack[--sp] : VR_DONE;
+      }
+    }
+
+    // ---- leaf ---------------------------------------------------------------------
+    if (cur & VR_LEAF_FLAG) {
+      const uint32_t first = (cur & 0x7fffffffu) >> 4, count = cur & 15u;
+      for (uint32_t k = 0; k < count; ++k) {
+        const uint32_t i = first + k;
+        if (GEO == 0) {
+          const float4 P = __ldg(&sc.primA[i]);
+          const float4 N = __ldg(&sc.primB[i]);
+          testDisk(P, N, i, org, dir, best);
+        } else {
+          const float4 a = __ldg(&sc.primA[i]), b = __ldg(&sc.primB[i]), c = __ldg(&sc.primC[i]);
+          testTri({a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, 1u, i, __float_as_uint(a.w),
+                  org, dir, best, nullptr);
+        }
+      }
+      wPrims += count;
+      cur = sp ? stack[--sp] : VR_DONE;
+    }
+
+    // ---- finished: publish the hit, free the lane ---------------------------------
+    if (slot != VR_INVALID_ID && cur == VR_DONE) {
+      __stcs(&p.pool.hit[slot], make_float4(best.t, __uint_as_float(best.prim),
+                                            __uint_as_float(best.geom), 0.f));
+      slot = VR_INVALID_ID;
     }
   }
-  // boundary box (geomID 0): wins ties against geometry
-#pragma unroll 1
-  for (uint32_t i = 0; i < 8; ++i) {
-    V3 v0 = {sc.btri[i][0][0], sc.btri[i][0][1], sc.btri[i][0][2]};
-    V3 v1 = {sc.btri[i][1][0], sc.btri[i][1][1], sc.btri[i][1][2]};
-    V3 v2 = {sc.btri[i][2][0], sc.btri[i][2][1], sc.btri[i][2][2]};
-    testTri(v0, v1, v2, 0u, i, i, org, dir, best, &bng);
+
+  if (p.work) {
+    unsigned long long a = warpSum((unsigned long long)wNodes),
+                       b = warpSum((unsigned long long)wPrims);
+    if (lane == 0) {
+      atomicAdd(&p.work[0], a);
+      atomicAdd(&p.work[1], b);
+    }
   }
+}
+
+cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s) {
+  if (p.numSlots == 0)
+    return cudaSuccess;
+  static int perSM[2] = {0, 0};
+  const int g = p.scene.geoType ? 1 : 0;
+  if (perSM[g] == 0) {
+    cudaError_t e = g ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[g],
+                                                                     traverseKernel<1>, 128, 0)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[g],
+                                                                     traverseKernel<0>, 128, 0);
+    if (e != cudaSuccess)
+      return e;
+    if (perSM[g] < 1)
+      perSM[g] = 1;
+  }
+  unsigned want = (p.numSlots + 127u) / 128u;
+  unsigned grid = (unsigned)(numSMs * perSM[g]);
+  if (want < grid)
+    grid = want;
+  if (g)
+    traverseKernel<1><<<grid, 128, 0, s>>>(p);
+  else
+    traverseKernel<0><<<grid, 128, 0, s>>>(p);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
@@ -101,7 +231,14 @@ __device__ __forceinline__ void intersectScene(const DeviceScene &sc, const V3 &
 // ---------------------------------------------------------------------------
 template <int D>
 __device__ __forceinline__ bool boundaryHit(const DeviceScene &sc, V3 &org, V3 &rayDirection,
-                                            V3 &dir, const V3 &ng, uint32_t primID, float t) {
+                                            V3 &dir, uint32_t primID, float t) {
+  // unnormalised triangle normal as the intersector reports it
+  V3 v0 = {sc.btri[primID][0][0], sc.btri[primID][0][1], sc.btri[primID][0][2]};
+  V3 v1 = {sc.btri[primID][1][0], sc.btri[primID][1][1], sc.btri[primID][1][2]};
+  V3 v2 = {sc.btri[primID][2][0], sc.btri[primID][2][1], sc.btri[primID][2][2]};
+  V3 e1 = {v0.x - v1.x, v0.y - v1.y, v0.z - v1.z};
+  V3 e2 = {v2.x - v0.x, v2.y - v0.y, v2.z - v0.z};
+  V3 ng = cross(e2, e1);
   V3 impact = {org.x + dir.x * t, org.y + dir.y * t, org.z + dir.z * t};
   if (dot(dir, ng) > 0.f) {
     org = impact;
@@ -136,86 +273,145 @@ __device__ __forceinline__ unsigned long long toFixed(float w) {
   return (unsigned long long)(long long)(w * VR_FIXED_SCALE);
 }
 
-__device__ __forceinline__ unsigned long long warpSum(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    v += __shfl_down_sync(0xffffffffu, v, o);
-  return v;
+// fetches the next ray index (warp-aggregated) and samples the source;
+// returns false when the job's rays are exhausted.  Must be reached by the
+// whole warp.
+template <int D>
+__device__ __forceinline__ bool regenerate(const TraceParams &p, bool want, uint64_t &idx,
+                                           Rng &rng, V3 &org, V3 &rayDirection, V3 &dir) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned mask = __ballot_sync(0xffffffffu, want);
+  if (!mask)
+    return false;
+  const int leader = __ffs(mask) - 1;
+  unsigned long long base = 0;
+  if ((int)lane == leader)
+    base = atomicAdd(p.rayCursor, (unsigned long long)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (!want)
+    return false;
+  const unsigned long long off = base + __popc(mask & ((1u << lane) - 1u));
+  if (off >= p.idxEnd - p.idxBegin)
+    return false;
+  idx = p.idxBegin + off;
+  rng.init(p.seed, p.stream, idx);
+  sourceSample<D>(p.src, p.ee, rng, org, rayDirection);
+  dir = fillDir<D>(rayDirection);
+  return true;
+}
+
+template <int D>
+__device__ __forceinline__ void storeRay(const RayPool &pool, uint32_t s, const V3 &org,
+                                         const V3 &dir, const V3 &rayDirection, float w,
+                                         const Rng &rng, uint64_t idx, uint32_t numReflections,
+                                         uint32_t boundaryHits, bool hitFromBack) {
+  pool.od0[s] = make_float4(org.x, org.y, org.z, dir.x);
+  pool.od1[s] = make_float2(dir.y, dir.z);
+  pool.rng[s] = rng.save();
+  pool.meta[s] = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
+                            boundaryHits | (hitFromBack ? 0x80000000u : 0u));
+  pool.weight[s] = w;
+  if (D == 2)
+    pool.dir3[s] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f);
 }
 
 // ---------------------------------------------------------------------------
-// persistent trace kernel
+// init: fill the pool with the first rays of the shard
+// ---------------------------------------------------------------------------
+template <int D> __global__ void __launch_bounds__(256) initPoolKernel(const TraceParams p) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool inRange = s < p.numSlots;
+  uint64_t idx = 0;
+  Rng rng;
+  rng.init(0, 0, 0);
+  V3 org = {0.f, 0.f, 0.f}, rd = {0.f, 0.f, 0.f}, dir = {0.f, 0.f, 0.f};
+  const bool ok = regenerate<D>(p, inRange, idx, rng, org, rd, dir);
+  if (!inRange)
+    return;
+  if (ok) {
+    storeRay<D>(p.pool, s, org, dir, rd, 1.f, rng, idx, 0u, 0u, false);
+    atomicAdd(p.liveCount, 1u);
+  } else {
+    p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
+  }
+}
+
+cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s) {
+  if (p.numSlots == 0)
+    return cudaSuccess;
+  unsigned grid = (p.numSlots + 255u) / 256u;
+  if (p.scene.D == 2)
+    initPoolKernel<2><<<grid, 256, 0, s>>>(p);
+  else
+    initPoolKernel<3><<<grid, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// shade: rayTraceKernel.hpp:169-333 for the hit of every live slot, then
+// regeneration of finished slots
 // ---------------------------------------------------------------------------
 template <int D, int GEO>
-__global__ void __launch_bounds__(128) traceKernel(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned ltMask = (1u << lane) - 1u;
-  const uint64_t numRays = p.idxEnd - p.idxBegin;
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ unsigned int shCount[12];
+  if (threadIdx.x < 12)
+    shCount[threadIdx.x] = 0u;
+  if (s == 0)
+    *p.slotCursor = 0u;  // for the traverse kernel that follows
+  __syncthreads();
 
-  // per-lane ray state
-  bool alive = false;
-  bool hitFromBack = false;
-  V3 org, dir, rayDirection;
+  unsigned cTraces = 0, cMiss = 0, cGeo = 0, cBnd = 0, cRefl = 0, cTerm = 0, wNb = 0, wFlux = 0;
+  bool live = false, finish = false;
+  float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
+  if (s < p.numSlots)
+    a = p.pool.od0[s];
+  live = !slotEmpty(a);
+
+  V3 org = {a.x, a.y, a.z}, dir = {0.f, 0.f, 0.f}, rayDirection = {0.f, 0.f, 0.f};
   float w = 0.f;
-  unsigned numReflections = 0, boundaryHits = 0;
+  uint64_t idx = 0;
+  uint32_t numReflections = 0, boundaryHits = 0;
+  bool hitFromBack = false;
   Rng rng;
-  // TraceInfo counters (rayTraceKernel.hpp:49-55)
-  unsigned long long cTraces = 0, cMiss = 0, cGeo = 0, cBnd = 0, cRefl = 0, cTerm = 0;
-  unsigned wNodes = 0, wPrims = 0, wNb = 0, wFlux = 0;
-  bool exhausted = false;
+  rng.init(0, 0, 0);
 
-  for (;;) {
-    // ---- regenerate finished lanes (warp-aggregated cursor fetch) ----------
-    unsigned dead = __ballot_sync(0xffffffffu, !alive);
-    if (dead && !exhausted) {
-      unsigned nDead = __popc(dead);
-      int leader = __ffs(dead) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader)
-        base = atomicAdd(p.rayCursor, (unsigned long long)nDead);
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (base + nDead >= numRays)
-        exhausted = true;  // warp-uniform
-      if (!alive) {
-        unsigned long long off = base + __popc(dead & ltMask);
-        if (off < numRays) {
-          uint64_t idx = p.idxBegin + off;
-          rng.init(p.seed, p.stream, idx);
-          w = 1.f;  // getInitialRayWeight, raySource.hpp:18
-          sourceSample<D>(p.src, p.ee, rng, org, rayDirection);
-          dir = fillDir<D>(rayDirection);
-          numReflections = 0;
-          boundaryHits = 0;
-          hitFromBack = false;
-          alive = true;
-        }
-      }
+  if (live) {
+    const float2 b = p.pool.od1[s];
+    dir = {a.w, b.x, b.y};
+    if (D == 2) {
+      const float4 r = p.pool.dir3[s];
+      rayDirection = {r.x, r.y, r.z};
+    } else {
+      rayDirection = dir;
     }
-    if (!__any_sync(0xffffffffu, alive))
-      break;
-    if (alive) {
-    // ---- one trace step -----------------------------------------------------
-    Hit h;
-    V3 bng = {0.f, 0.f, 0.f};
-    intersectScene<GEO>(sc, org, dir, h, bng, wNodes, wPrims);
+    const float4 hv = __ldcs(&p.pool.hit[s]);
+    const float ht = hv.x;
+    const uint32_t hprim = __float_as_uint(hv.y), hgeom = __float_as_uint(hv.z);
+    const uint4 meta = p.pool.meta[s];
+    idx = (uint64_t)meta.x | ((uint64_t)meta.y << 32);
+    numReflections = meta.z;
+    boundaryHits = meta.w & 0x7fffffffu;
+    hitFromBack = (meta.w >> 31) != 0u;
+    w = p.pool.weight[s];
+
     ++cTraces;
-    bool finish = false;
-    if (h.geom == VR_INVALID_ID) {  // :172
+    if (hgeom == VR_INVALID_ID) {  // :172
       ++cMiss;
       finish = true;
-    } else if (h.geom == 0u) {  // :206-214
+    } else if (hgeom == 0u) {  // :206-214
       if (++boundaryHits > p.maxBoundaryHits) {
         ++cTerm;
         finish = true;
-      } else if (!boundaryHit<D>(sc, org, rayDirection, dir, bng, h.prim, h.t)) {
+      } else if (!boundaryHit<D>(sc, org, rayDirection, dir, hprim, ht)) {
         finish = true;
       }
     } else {
-      V3 hitPoint = {org.x + dir.x * h.t, org.y + dir.y * h.t, org.z + dir.z * h.t};
-      float4 N4 = __ldg(&sc.primN[h.prim]);
-      V3 gn = {N4.x, N4.y, N4.z};
-      bool backface = dot(rayDirection, gn) > 0.f;  // :224
+      const V3 hitPoint = {org.x + dir.x * ht, org.y + dir.y * ht, org.z + dir.z * ht};
+      const float4 N4 = __ldg(&sc.primN[hprim]);
+      const V3 gn = {N4.x, N4.y, N4.z};
+      const bool backface = dot(rayDirection, gn) > 0.f;  // :224
       if (backface) {
         if (GEO == 0 && !hitFromBack) {  // :226-241 let the ray through once
           hitFromBack = true;
@@ -226,15 +422,15 @@ __global__ void __launch_bounds__(128) traceKernel(const __grid_constant__ Trace
         }
       } else {
         ++cGeo;
-        unsigned long long wf = toFixed(w);
-        atomicAdd(&p.flux[h.prim], wf);  // :297-306 surfaceCollision
+        const unsigned long long wf = toFixed(w);
+        atomicAdd(&p.flux[hprim], wf);  // :297-306 surfaceCollision
         ++wFlux;
         if (GEO == 0) {  // :271-280 neighbour spread
-          uint32_t k0 = __ldg(&sc.nbOff[h.prim]), k1 = __ldg(&sc.nbOff[h.prim + 1]);
+          const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
           for (uint32_t k = k0; k < k1; ++k) {
-            uint32_t id = __ldg(&sc.nbIdx[k]);
-            float4 P = __ldg(&sc.primA[id]);
-            float4 Nn = __ldg(&sc.primB[id]);
+            const uint32_t id = __ldg(&sc.nbIdx[k]);
+            const float4 P = __ldg(&sc.primA[id]);
+            const float4 Nn = __ldg(&sc.primB[id]);
             ++wNb;
             if (checkLocal(P, Nn, org, dir)) {
               atomicAdd(&p.flux[id], wf);
@@ -242,8 +438,9 @@ __global__ void __launch_bounds__(128) traceKernel(const __grid_constant__ Trace
             }
           }
         }
-        V3 newDir = surfaceReflection<D>(p.particle, rayDirection, gn, rng);  // :310
-        w -= w * p.particle.sticking;                                         // :316
+        rng.load(p.pool.rng[s], p.seed, p.stream, idx);
+        const V3 newDir = surfaceReflection<D>(p.particle, rayDirection, gn, rng);  // :310
+        w -= w * p.particle.sticking;                                               // :316
         if (w <= 0.f) {
           finish = true;
         } else if (++numReflections > p.maxReflections) {
@@ -252,7 +449,7 @@ __global__ void __launch_bounds__(128) traceKernel(const __grid_constant__ Trace
         } else {
           // :435-460 rejectionControl, thresholds 0.1 / 0.3 of the initial weight
           if (w < 0.1f) {
-            float kill = 1.f - w / 0.3f;
+            const float kill = 1.f - w / 0.3f;
             if (rng.f() < kill)
               finish = true;
             else
@@ -264,67 +461,103 @@ __global__ void __launch_bounds__(128) traceKernel(const __grid_constant__ Trace
             dir = fillDir<D>(rayDirection);
           }
         }
+        if (!finish)
+          p.pool.rng[s] = rng.save();
       }
     }
     if (finish) {
       cBnd += boundaryHits;
       cRefl += numReflections;
-      alive = false;
     }
-    }  // alive
   }
 
-  // ---- counters: warp reduce, one atomic per warp --------------------------
-  cTraces = warpSum(cTraces);
-  cMiss = warpSum(cMiss);
-  cGeo = warpSum(cGeo);
-  cBnd = warpSum(cBnd);
-  cRefl = warpSum(cRefl);
-  cTerm = warpSum(cTerm);
-  if (lane == 0) {
-    atomicAdd(&p.counters[1], cTraces);
-    atomicAdd(&p.counters[2], cMiss);
-    atomicAdd(&p.counters[3], cGeo);
-    atomicAdd(&p.counters[5], cBnd);
-    atomicAdd(&p.counters[6], cRefl);
-    atomicAdd(&p.counters[7], cTerm);
+  // ---- regenerate finished slots in place ------------------------------------------
+  const bool regen = regenerate<D>(p, live && finish, idx, rng, org, rayDirection, dir);
+  if (live) {
+    if (!finish) {
+      p.pool.od0[s] = make_float4(org.x, org.y, org.z, dir.x);
+      p.pool.od1[s] = make_float2(dir.y, dir.z);
+      p.pool.meta[s] = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
+                                  boundaryHits | (hitFromBack ? 0x80000000u : 0u));
+      p.pool.weight[s] = w;
+      if (D == 2)
+        p.pool.dir3[s] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f);
+    } else if (regen) {
+      storeRay<D>(p.pool, s, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
+    } else {
+      p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
+    }
   }
-  if (p.work) {
-    unsigned long long a = warpSum((unsigned long long)wNodes), b = warpSum((unsigned long long)wPrims),
-                       c = warpSum((unsigned long long)wNb), d = warpSum((unsigned long long)wFlux);
-    if (lane == 0) {
-      atomicAdd(&p.work[0], a);
-      atomicAdd(&p.work[1], b);
-      atomicAdd(&p.work[2], c);
-      atomicAdd(&p.work[3], d);
+  const bool stillLive = live && (!finish || regen);
+
+  // ---- counters: warp -> block -> one global atomic per block and counter ----------
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned vals[9] = {cTraces, cMiss, cGeo, cBnd, cRefl, cTerm, stillLive ? 1u : 0u, wNb, wFlux};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    unsigned v = vals[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0 && v)
+      atomicAdd(&shCount[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    const unsigned v = shCount[threadIdx.x];
+    if (v) {
+      unsigned long long *cnt = p.counters + (size_t)(blockIdx.x % VR_COUNTER_COPIES) * 8;
+      switch (threadIdx.x) {
+      case 0:
+        atomicAdd(&cnt[1], (unsigned long long)v);
+        break;
+      case 1:
+        atomicAdd(&cnt[2], (unsigned long long)v);
+        break;
+      case 2:
+        atomicAdd(&cnt[3], (unsigned long long)v);
+        break;
+      case 3:
+        atomicAdd(&cnt[5], (unsigned long long)v);
+        break;
+      case 4:
+        atomicAdd(&cnt[6], (unsigned long long)v);
+        break;
+      case 5:
+        atomicAdd(&cnt[7], (unsigned long long)v);
+        break;
+      case 6:
+        atomicAdd(p.liveCount, v);
+        break;
+      case 7:
+        if (p.work)
+          atomicAdd(&p.work[2], (unsigned long long)v);
+        break;
+      default:
+        if (p.work)
+          atomicAdd(&p.work[3], (unsigned long long)v);
+        break;
+      }
     }
   }
 }
 
-template <int D, int GEO>
-static cudaError_t launchTraceT(const TraceParams &p, int numSMs, cudaStream_t s) {
-  int perSM = 0;
-  cudaError_t e =
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<D, GEO>, 128, 0);
-  if (e != cudaSuccess)
-    return e;
-  if (perSM < 1)
-    perSM = 1;
-  uint64_t numRays = p.idxEnd - p.idxBegin;
-  uint64_t want = (numRays + 127) / 128;
-  uint64_t grid = (uint64_t)numSMs * perSM;
-  if (want < grid)
-    grid = want ? want : 1;
-  traceKernel<D, GEO><<<(unsigned)grid, 128, 0, s>>>(p);
+cudaError_t launchShade(const TraceParams &p, cudaStream_t s) {
+  if (p.numSlots == 0)
+    return cudaSuccess;
+  unsigned grid = (p.numSlots + 255u) / 256u;
+  if (p.scene.geoType == 0) {
+    if (p.scene.D == 2)
+      shadeKernel<2, 0><<<grid, 256, 0, s>>>(p);
+    else
+      shadeKernel<3, 0><<<grid, 256, 0, s>>>(p);
+  } else {
+    if (p.scene.D == 2)
+      shadeKernel<2, 1><<<grid, 256, 0, s>>>(p);
+    else
+      shadeKernel<3, 1><<<grid, 256, 0, s>>>(p);
+  }
   return cudaGetLastError();
-}
-
-cudaError_t launchTrace(const TraceParams &p, int numSMs, cudaStream_t s, int *launches) {
-  if (launches)
-    *launches += 1;
-  if (p.scene.geoType == 0)
-    return p.scene.D == 2 ? launchTraceT<2, 0>(p, numSMs, s) : launchTraceT<3, 0>(p, numSMs, s);
-  return p.scene.D == 2 ? launchTraceT<2, 1>(p, numSMs, s) : launchTraceT<3, 1>(p, numSMs, s);
 }
 
 // ---------------------------------------------------------------------------
@@ -341,7 +574,7 @@ __global__ void diskBoundsKernel(const float4 *xyzr, const float4 *nrm, uint32_t
   for (int a = 0; a < 3; ++a) {
     float f = nn > 0.f ? 1.f - nv[a] * nv[a] / nn : 1.f;
     float e = P.w * sqrtf(fmaxf(f, 0.f));
-    float pad = 2e-4f * P.w + 1e-6f * fabsf(c[a]);
+    float pad = 2e-4f * P.w + 2e-6f * fabsf(c[a]);
     l[a] = c[a] - e - pad;
     h[a] = c[a] + e + pad;
   }
@@ -360,7 +593,7 @@ __global__ void triBoundsKernel(const float4 *v0, const float4 *v1, const float4
   float h[3] = {fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)),
                 fmaxf(a.z, fmaxf(b.z, c.z))};
   for (int k = 0; k < 3; ++k) {
-    float pad = 2e-5f * (h[k] - l[k]) + 1e-6f * fmaxf(fabsf(l[k]), fabsf(h[k])) + 1e-30f;
+    float pad = 2e-5f * (h[k] - l[k]) + 2e-6f * fmaxf(fabsf(l[k]), fabsf(h[k])) + 1e-30f;
     l[k] -= pad;
     h[k] += pad;
   }
@@ -382,28 +615,41 @@ cudaError_t launchTriBounds(const float4 *v0, const float4 *v1, const float4 *v2
 }
 
 // ---------------------------------------------------------------------------
-// parity / debug kernels
+// parity / debug kernels.  vr_debug_intersect runs the PRODUCTION traverse
+// kernel on caller rays loaded into the pool, then converts the hits.
 // ---------------------------------------------------------------------------
-template <int GEO>
-__global__ void debugIntersectKernel(DeviceScene sc, const float *rays, uint32_t m, uint32_t *geom,
-                                     uint32_t *prim, float *t, uint32_t nbCap, uint32_t *nbCount,
-                                     uint32_t *nbOut, const uint32_t *sortedToOrig) {
+__global__ void debugLoadRaysKernel(RayPool pool, const float *rays, uint32_t m) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m)
     return;
-  V3 org = {rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]};
-  V3 dir = {rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]};
-  Hit h;
-  V3 bng;
-  unsigned a = 0, b = 0;
-  intersectScene<GEO>(sc, org, dir, h, bng, a, b);
-  geom[i] = h.geom;
-  prim[i] = h.geom == VR_INVALID_ID ? VR_INVALID_ID : h.orig;
-  t[i] = h.t;
+  pool.od0[i] = make_float4(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2], rays[6 * i + 3]);
+  pool.od1[i] = make_float2(rays[6 * i + 4], rays[6 * i + 5]);
+}
+cudaError_t launchDebugLoadRays(const RayPool &pool, const float *rays, uint32_t m,
+                                cudaStream_t s) {
+  if (m)
+    debugLoadRaysKernel<<<(m + 255) / 256, 256, 0, s>>>(pool, rays, m);
+  return cudaGetLastError();
+}
+
+__global__ void debugReadHitsKernel(DeviceScene sc, RayPool pool, uint32_t m, uint32_t *geom,
+                                    uint32_t *prim, float *t, uint32_t nbCap, uint32_t *nbCount,
+                                    uint32_t *nbOut, const uint32_t *sortedToOrig) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m)
+    return;
+  const float4 a = pool.od0[i];
+  const float2 b = pool.od1[i];
+  const float4 hv = pool.hit[i];
+  const uint32_t hprim = __float_as_uint(hv.y), hgeom = __float_as_uint(hv.z);
+  geom[i] = hgeom;
+  prim[i] = hgeom == VR_INVALID_ID ? VR_INVALID_ID : (hgeom == 0u ? hprim : sortedToOrig[hprim]);
+  t[i] = hv.x;
   if (nbCount) {
+    V3 org = {a.x, a.y, a.z}, dir = {a.w, b.x, b.y};
     uint32_t cnt = 0;
-    if (GEO == 0 && h.geom == 1u) {
-      uint32_t k0 = sc.nbOff[h.prim], k1 = sc.nbOff[h.prim + 1];
+    if (sc.geoType == 0 && hgeom == 1u) {
+      uint32_t k0 = sc.nbOff[hprim], k1 = sc.nbOff[hprim + 1];
       for (uint32_t k = k0; k < k1; ++k) {
         uint32_t id = sc.nbIdx[k];
         if (checkLocal(sc.primA[id], sc.primB[id], org, dir)) {
@@ -416,19 +662,13 @@ __global__ void debugIntersectKernel(DeviceScene sc, const float *rays, uint32_t
     nbCount[i] = cnt;
   }
 }
-
-cudaError_t launchDebugIntersect(const DeviceScene &sc, const float *rays, uint32_t m,
-                                 uint32_t *geom, uint32_t *prim, float *t, uint32_t nbCap,
-                                 uint32_t *nbCount, uint32_t *nbOut, const uint32_t *sortedToOrig,
-                                 cudaStream_t s) {
-  if (!m)
-    return cudaSuccess;
-  if (sc.geoType == 0)
-    debugIntersectKernel<0><<<(m + 127) / 128, 128, 0, s>>>(sc, rays, m, geom, prim, t, nbCap,
-                                                             nbCount, nbOut, sortedToOrig);
-  else
-    debugIntersectKernel<1><<<(m + 127) / 128, 128, 0, s>>>(sc, rays, m, geom, prim, t, nbCap,
-                                                             nbCount, nbOut, sortedToOrig);
+cudaError_t launchDebugReadHits(const DeviceScene &sc, const RayPool &pool, uint32_t m,
+                                uint32_t *geom, uint32_t *prim, float *t, uint32_t nbCap,
+                                uint32_t *nbCount, uint32_t *nbOut, const uint32_t *sortedToOrig,
+                                cudaStream_t s) {
+  if (m)
+    debugReadHitsKernel<<<(m + 127) / 128, 128, 0, s>>>(sc, pool, m, geom, prim, t, nbCap,
+                                                         nbCount, nbOut, sortedToOrig);
   return cudaGetLastError();
 }
 
