@@ -787,7 +787,7 @@ int vr_debug_intersect(vr_ctx *ctx, const float *rays, uint32_t m, uint32_t *geo
     p.liveCount = ctx->dSlotCursor + 1;
     p.work = nullptr;
     CKD(cudaMemsetAsync(ctx->dSlotCursor, 0, 2 * sizeof(unsigned int), ctx->stream));
-    CKD(launchDebugLoadRays(ctx->pool, dRays, m, ctx->stream));
+    CKD(launchDebugLoadRays(ctx->scene, ctx->pool, dRays, m, ctx->stream));
     CKD(launchTraverse(p, ctx->numSMs, ctx->stream));
     CKD(launchDebugReadHits(ctx->scene, ctx->pool, m, dGeom, dPrim, dT, wantNb ? nbCap : 0u,
                             wantNb ? dCnt : nullptr, dNb, ctx->bvh.sortedToOrig, ctx->stream));

@@ -95,8 +95,8 @@ cudaError_t launchTriBounds(const float4 *v0, const float4 *v1, const float4 *v2
 cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s);
 cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s);
 cudaError_t launchShade(const TraceParams &p, cudaStream_t s);
-cudaError_t launchDebugLoadRays(const RayPool &pool, const float *rays, uint32_t m,
-                                cudaStream_t s);
+cudaError_t launchDebugLoadRays(const DeviceScene &sc, const RayPool &pool, const float *rays,
+                                uint32_t m, cudaStream_t s);
 cudaError_t launchDebugReadHits(const DeviceScene &sc, const RayPool &pool, uint32_t m,
                                 uint32_t *geom, uint32_t *prim, float *t, uint32_t nbCap,
                                 uint32_t *nbCount, uint32_t *nbOut, const uint32_t *sortedToOrig,

@@ -51,6 +51,16 @@ __device__ __forceinline__ void boundaryTest(const DeviceScene &sc, const V3 &or
   }
 }
 
+// closest boundary hit of a fresh ray, stored as the traversal's initial best
+__device__ __forceinline__ void storeBoundaryHit(const DeviceScene &sc, const RayPool &pool,
+                                                 uint32_t s, const V3 &org, const V3 &dir) {
+  Hit best;
+  best.t = 3.402823466e+38f;
+  best.geom = best.prim = best.orig = VR_INVALID_ID;
+  boundaryTest(sc, org, dir, best);
+  pool.hit[s] = make_float4(best.t, __uint_as_float(best.prim), __uint_as_float(best.geom), 0.f);
+}
+
 __device__ __forceinline__ unsigned long long warpSum(unsigned long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -103,15 +113,19 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
             slot = s;
             org = {a.x, a.y, a.z};
             dir = {a.w, b.x, b.y};
-            ix = 1.f / dir.x;
-            iy = 1.f / dir.y;
-            iz = 1.f / dir.z;
+            // reciprocal for the slab tests only; a zero component becomes a
+            // huge finite slope so that lo*ix - org*ix keeps the right sign
+            ix = 1.f / (fabsf(dir.x) > 1e-20f ? dir.x : copysignf(1e-20f, dir.x));
+            iy = 1.f / (fabsf(dir.y) > 1e-20f ? dir.y : copysignf(1e-20f, dir.y));
+            iz = 1.f / (fabsf(dir.z) > 1e-20f ? dir.z : copysignf(1e-20f, dir.z));
             ox = -org.x * ix;
             oy = -org.y * iy;
             oz = -org.z * iz;
-            best.t = 3.402823466e+38f;
-            best.geom = best.prim = best.orig = VR_INVALID_ID;
-            boundaryTest(sc, org, dir, best);
+            // the shade / init kernel already intersected the boundary box
+            const float4 h0 = __ldcs(&p.pool.hit[s]);
+            best.t = h0.x;
+            best.prim = best.orig = __float_as_uint(h0.y);
+            best.geom = __float_as_uint(h0.z);
             sp = 0;
             cur = sc.numPrims ? sc.rootRef : VR_DONE;
           }
@@ -330,6 +344,7 @@ template <int D> __global__ void __launch_bounds__(256) initPoolKernel(const Tra
     return;
   if (ok) {
     storeRay<D>(p.pool, s, org, dir, rd, 1.f, rng, idx, 0u, 0u, false);
+    storeBoundaryHit(p.scene, p.pool, s, org, dir);
     atomicAdd(p.liveCount, 1u);
   } else {
     p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
@@ -487,6 +502,8 @@ __global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ Trace
     } else {
       p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
     }
+    if (!finish || regen)
+      storeBoundaryHit(sc, p.pool, s, org, dir);
   }
   const bool stillLive = live && (!finish || regen);
 
@@ -618,17 +635,20 @@ cudaError_t launchTriBounds(const float4 *v0, const float4 *v1, const float4 *v2
 // parity / debug kernels.  vr_debug_intersect runs the PRODUCTION traverse
 // kernel on caller rays loaded into the pool, then converts the hits.
 // ---------------------------------------------------------------------------
-__global__ void debugLoadRaysKernel(RayPool pool, const float *rays, uint32_t m) {
+__global__ void debugLoadRaysKernel(DeviceScene sc, RayPool pool, const float *rays, uint32_t m) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m)
     return;
-  pool.od0[i] = make_float4(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2], rays[6 * i + 3]);
-  pool.od1[i] = make_float2(rays[6 * i + 4], rays[6 * i + 5]);
+  V3 org = {rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]};
+  V3 dir = {rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]};
+  pool.od0[i] = make_float4(org.x, org.y, org.z, dir.x);
+  pool.od1[i] = make_float2(dir.y, dir.z);
+  storeBoundaryHit(sc, pool, i, org, dir);
 }
-cudaError_t launchDebugLoadRays(const RayPool &pool, const float *rays, uint32_t m,
-                                cudaStream_t s) {
+cudaError_t launchDebugLoadRays(const DeviceScene &sc, const RayPool &pool, const float *rays,
+                                uint32_t m, cudaStream_t s) {
   if (m)
-    debugLoadRaysKernel<<<(m + 255) / 256, 256, 0, s>>>(pool, rays, m);
+    debugLoadRaysKernel<<<(m + 255) / 256, 256, 0, s>>>(sc, pool, rays, m);
   return cudaGetLastError();
 }
 
