@@ -45,7 +45,7 @@ struct vr_ctx {
   unsigned long long *dCounterCopies = nullptr;  // VR_COUNTER_COPIES x 8
   unsigned int *hLive = nullptr;            // pinned ring of live counts
   cudaEvent_t liveEv[4] = {nullptr, nullptr, nullptr, nullptr};
-  RayPool pool{};
+  RayPool pool{}, pool2{};
   unsigned long long *dWork = nullptr;
   size_t resultWords = 0;
   int numParticles = 0;
@@ -96,34 +96,44 @@ static void freeResults(vr_ctx *c) {
   c->numParticles = 0;
 }
 
-static void freePool(vr_ctx *c) {
-  cudaFree(c->pool.od0);
-  cudaFree(c->pool.od1);
-  cudaFree(c->pool.hit);
-  cudaFree(c->pool.rng);
-  cudaFree(c->pool.meta);
-  cudaFree(c->pool.weight);
-  cudaFree(c->pool.dir3);
-  c->pool = RayPool{};
+static void freeOnePool(RayPool &q) {
+  cudaFree(q.od0);
+  cudaFree(q.od1);
+  cudaFree(q.hit);
+  cudaFree(q.rng);
+  cudaFree(q.meta);
+  cudaFree(q.weight);
+  cudaFree(q.dir3);
+  q = RayPool{};
 }
-
+static void freePool(vr_ctx *c) {
+  freeOnePool(c->pool);
+  freeOnePool(c->pool2);
+}
+static cudaError_t allocOnePool(RayPool &q, uint32_t slots) {
+  cudaError_t e;
+  if ((e = cudaMalloc(&q.od0, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.od1, sizeof(float2) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.hit, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.rng, sizeof(uint4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.meta, sizeof(uint4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.weight, sizeof(float) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.dir3, sizeof(float4) * (size_t)slots)) != cudaSuccess)
+    return e;
+  q.capacity = slots;
+  return cudaSuccess;
+}
+// two pools: the tail of a trace compacts survivors from one into the other
 static cudaError_t ensurePool(vr_ctx *c, uint32_t slots) {
-  if (c->pool.capacity >= slots && c->pool.od0)
+  if (c->pool.capacity >= slots && c->pool.od0 && c->pool2.od0)
     return cudaSuccess;
   freePool(c);
-  cudaError_t e;
-  if ((e = cudaMalloc(&c->pool.od0, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
-      (e = cudaMalloc(&c->pool.od1, sizeof(float2) * (size_t)slots)) != cudaSuccess ||
-      (e = cudaMalloc(&c->pool.hit, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
-      (e = cudaMalloc(&c->pool.rng, sizeof(uint4) * (size_t)slots)) != cudaSuccess ||
-      (e = cudaMalloc(&c->pool.meta, sizeof(uint4) * (size_t)slots)) != cudaSuccess ||
-      (e = cudaMalloc(&c->pool.weight, sizeof(float) * (size_t)slots)) != cudaSuccess ||
-      (e = cudaMalloc(&c->pool.dir3, sizeof(float4) * (size_t)slots)) != cudaSuccess) {
+  cudaError_t e = allocOnePool(c->pool, slots);
+  if (e == cudaSuccess)
+    e = allocOnePool(c->pool2, slots);
+  if (e != cudaSuccess)
     freePool(c);
-    return e;
-  }
-  c->pool.capacity = slots;
-  return cudaSuccess;
+  return e;
 }
 
 __global__ void reduceCountersKernel(const unsigned long long *copies, unsigned long long *out) {
@@ -179,7 +189,7 @@ int vr_ctx_create(int cudaDevice, vr_ctx **out) {
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->dCursor, sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->dSlotCursor, 2 * sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->dSlotCursor, 4 * sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaMalloc(&ctx->dCounterCopies,
                       VR_COUNTER_COPIES * 8 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMallocHost(&ctx->hLive, 4 * sizeof(unsigned int))) != cudaSuccess ||
@@ -511,10 +521,13 @@ static int fillParams(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_
   p.maxReflections = cfg->maxReflections;
   p.maxBoundaryHits = cfg->maxBoundaryHits;
   p.pool = ctx->pool;
+  p.poolOut = ctx->pool2;
+  p.compact = 0;
   p.numSlots = 0;
   p.rayCursor = ctx->dCursor;
   p.slotCursor = ctx->dSlotCursor;
   p.liveCount = ctx->dSlotCursor + 1;
+  p.slotCount = ctx->dSlotCursor + 2;
   p.work = ctx->countWork ? ctx->dWork : nullptr;
   return VR_OK;
 }
@@ -558,27 +571,51 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
     if (p.idxEnd == p.idxBegin)
       continue;
     CK(cudaMemsetAsync(ctx->dCursor, 0, sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(ctx->dSlotCursor, 0, 2 * sizeof(unsigned int), ctx->stream));
+    {
+      const unsigned int ctrl[4] = {0u, 0u, slots, 0u};
+      CK(cudaMemcpyAsync(ctx->dSlotCursor, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice,
+                         ctx->stream));
+    }
     CK(cudaMemsetAsync(ctx->dCounterCopies, 0, VR_COUNTER_COPIES * 8 * sizeof(unsigned long long),
                        ctx->stream));
     CK(launchInitPool(p, ctx->stream));
-    ++ctx->kernelLaunches;
-    // wavefront iterations; the live count of iteration i is read back two
-    // iterations later so the device never waits for the host
+    CK(launchFlip(ctx->dSlotCursor, 0, ctx->stream));
+    ctx->kernelLaunches += 2;
+    // Wavefront iterations.  The live count of iteration i is read back two
+    // iterations later so the device never waits for the host.  Once a count
+    // below the pool size shows that the source is exhausted, the shade kernel
+    // compacts the survivors into the other pool and the launches shrink.
+    bool compact = false, compacted = false;
+    uint32_t bound = slots;  // upper bound of the survivors (lagging read-back)
+    int cur = 0;
     for (int it = 0;; ++it) {
+      p.pool = cur ? ctx->pool2 : ctx->pool;
+      p.poolOut = cur ? ctx->pool : ctx->pool2;
+      p.compact = compact ? 1 : 0;
+      p.numSlots = compacted ? bound : slots;  // the first compacting pass reads every slot
       CK(launchTraverse(p, ctx->numSMs, ctx->stream));
       CK(launchShade(p, ctx->stream));
-      ctx->kernelLaunches += 2;
-      ++ctx->iterations;
       const int r = it & 3;
       CK(cudaMemcpyAsync(&ctx->hLive[r], p.liveCount, sizeof(unsigned int),
                          cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaEventRecord(ctx->liveEv[r], ctx->stream));
+      CK(launchFlip(ctx->dSlotCursor, p.compact, ctx->stream));
+      ctx->kernelLaunches += 3;
+      ++ctx->iterations;
+      if (compact) {
+        cur ^= 1;
+        compacted = true;
+      }
       if (it >= 2) {
         const int q = (it - 2) & 3;
         CK(cudaEventSynchronize(ctx->liveEv[q]));
-        if (ctx->hLive[q] == 0u)
+        const uint32_t live = ctx->hLive[q];
+        if (live == 0u)
           break;
+        if (live < slots) {
+          compact = true;
+          bound = std::min(bound, live);
+        }
       }
     }
     reduceCountersKernel<<<1, 32, 0, ctx->stream>>>(ctx->dCounterCopies,
@@ -785,8 +822,13 @@ int vr_debug_intersect(vr_ctx *ctx, const float *rays, uint32_t m, uint32_t *geo
     p.numSlots = m;
     p.slotCursor = ctx->dSlotCursor;
     p.liveCount = ctx->dSlotCursor + 1;
+    p.slotCount = ctx->dSlotCursor + 2;
     p.work = nullptr;
-    CKD(cudaMemsetAsync(ctx->dSlotCursor, 0, 2 * sizeof(unsigned int), ctx->stream));
+    {
+      const unsigned int ctrl[4] = {0u, 0u, m, 0u};
+      CKD(cudaMemcpyAsync(ctx->dSlotCursor, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice,
+                          ctx->stream));
+    }
     CKD(launchDebugLoadRays(ctx->scene, ctx->pool, dRays, m, ctx->stream));
     CKD(launchTraverse(p, ctx->numSMs, ctx->stream));
     CKD(launchDebugReadHits(ctx->scene, ctx->pool, m, dGeom, dPrim, dT, wantNb ? nbCap : 0u,

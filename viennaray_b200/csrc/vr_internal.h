@@ -57,14 +57,17 @@ struct RayPool {
 
 struct TraceParams {
   DeviceScene scene;
-  RayPool pool;
+  RayPool pool;     // slots read by traverse and shade
+  RayPool poolOut;  // shade, compact mode: survivors are appended here
+  int compact;      // 0: survivors stay in place; 1: append to poolOut
   vr_source_desc src;
   vr_particle_desc particle;
   float ee;  // 1 / (sourcePower + 1), raySourceRandom.hpp:21
   uint64_t idxBegin, idxEnd;
   uint32_t seed, stream;
   uint32_t maxReflections, maxBoundaryHits;
-  uint32_t numSlots;             // slots in use this launch (<= pool.capacity)
+  uint32_t numSlots;             // upper bound of the slots in use (sizes the grid)
+  const unsigned int *slotCount; // device: slots actually in use
   unsigned long long *flux;      // numPrims fixed-point sums (internal order)
   unsigned long long *counters;  // VR_COUNTER_COPIES x 8 TraceInfo counters
   unsigned long long *rayCursor; // rays handed out so far
@@ -95,6 +98,8 @@ cudaError_t launchTriBounds(const float4 *v0, const float4 *v1, const float4 *v2
 cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s);
 cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s);
 cudaError_t launchShade(const TraceParams &p, cudaStream_t s);
+// between iterations: resets the cursors; compact mode: slotCount = liveCount
+cudaError_t launchFlip(unsigned int *ctrl, int compact, cudaStream_t s);
 cudaError_t launchDebugLoadRays(const DeviceScene &sc, const RayPool &pool, const float *rays,
                                 uint32_t m, cudaStream_t s);
 cudaError_t launchDebugReadHits(const DeviceScene &sc, const RayPool &pool, uint32_t m,

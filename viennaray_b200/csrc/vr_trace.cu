@@ -76,9 +76,7 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
   const DeviceScene &sc = p.scene;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned ltMask = (1u << lane) - 1u;
-  const uint32_t numSlots = p.numSlots;
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    *p.liveCount = 0u;  // the shade kernel that follows counts survivors
+  const uint32_t numSlots = *p.slotCount;
 
   uint32_t slot = VR_INVALID_ID;
   V3 org = {0.f, 0.f, 0.f}, dir = {0.f, 0.f, 1.f};
@@ -373,14 +371,13 @@ __global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ Trace
   __shared__ unsigned int shCount[12];
   if (threadIdx.x < 12)
     shCount[threadIdx.x] = 0u;
-  if (s == 0)
-    *p.slotCursor = 0u;  // for the traverse kernel that follows
   __syncthreads();
+  const uint32_t numSlots = *p.slotCount;
 
   unsigned cTraces = 0, cMiss = 0, cGeo = 0, cBnd = 0, cRefl = 0, cTerm = 0, wNb = 0, wFlux = 0;
   bool live = false, finish = false;
   float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
-  if (s < p.numSlots)
+  if (s < numSlots)
     a = p.pool.od0[s];
   live = !slotEmpty(a);
 
@@ -388,7 +385,7 @@ __global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ Trace
   float w = 0.f;
   uint64_t idx = 0;
   uint32_t numReflections = 0, boundaryHits = 0;
-  bool hitFromBack = false;
+  bool hitFromBack = false, rngLoaded = false;
   Rng rng;
   rng.init(0, 0, 0);
 
@@ -454,6 +451,7 @@ __global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ Trace
           }
         }
         rng.load(p.pool.rng[s], p.seed, p.stream, idx);
+        rngLoaded = true;
         const V3 newDir = surfaceReflection<D>(p.particle, rayDirection, gn, rng);  // :310
         w -= w * p.particle.sticking;                                               // :316
         if (w <= 0.f) {
@@ -486,26 +484,52 @@ __global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ Trace
     }
   }
 
-  // ---- regenerate finished slots in place ------------------------------------------
+  // ---- regenerate finished slots; write survivors back (in place, or appended to
+  // the other pool when compacting the tail) ----------------------------------------
   const bool regen = regenerate<D>(p, live && finish, idx, rng, org, rayDirection, dir);
-  if (live) {
-    if (!finish) {
-      p.pool.od0[s] = make_float4(org.x, org.y, org.z, dir.x);
-      p.pool.od1[s] = make_float2(dir.y, dir.z);
-      p.pool.meta[s] = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
-                                  boundaryHits | (hitFromBack ? 0x80000000u : 0u));
-      p.pool.weight[s] = w;
-      if (D == 2)
-        p.pool.dir3[s] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f);
-    } else if (regen) {
-      storeRay<D>(p.pool, s, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
-    } else {
-      p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
+  const bool survive = live && (!finish || regen);
+  if (!p.compact) {
+    if (live) {
+      if (!finish) {
+        p.pool.od0[s] = make_float4(org.x, org.y, org.z, dir.x);
+        p.pool.od1[s] = make_float2(dir.y, dir.z);
+        p.pool.meta[s] = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
+                                    boundaryHits | (hitFromBack ? 0x80000000u : 0u));
+        p.pool.weight[s] = w;
+        if (D == 2)
+          p.pool.dir3[s] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f);
+      } else if (regen) {
+        storeRay<D>(p.pool, s, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
+      } else {
+        p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
+      }
+      if (survive)
+        storeBoundaryHit(sc, p.pool, s, org, dir);
     }
-    if (!finish || regen)
-      storeBoundaryHit(sc, p.pool, s, org, dir);
+  } else {
+    const unsigned m = __ballot_sync(0xffffffffu, survive);
+    if (m) {
+      const unsigned ln = threadIdx.x & 31u;
+      const int leader = __ffs(m) - 1;
+      unsigned base = 0;
+      if ((int)ln == leader)
+        base = atomicAdd(p.liveCount, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (survive) {
+        const uint32_t dst = base + __popc(m & ((1u << ln) - 1u));
+        if (!finish) {
+          if (!rngLoaded)
+            rng.load(p.pool.rng[s], p.seed, p.stream, idx);
+          storeRay<D>(p.poolOut, dst, org, dir, rayDirection, w, rng, idx, numReflections,
+                      boundaryHits, hitFromBack);
+        } else {
+          storeRay<D>(p.poolOut, dst, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
+        }
+        storeBoundaryHit(sc, p.poolOut, dst, org, dir);
+      }
+    }
   }
-  const bool stillLive = live && (!finish || regen);
+  const bool stillLive = survive && !p.compact;  // compact mode counted them above
 
   // ---- counters: warp -> block -> one global atomic per block and counter ----------
   const unsigned lane = threadIdx.x & 31u;
@@ -557,6 +581,18 @@ __global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ Trace
       }
     }
   }
+}
+
+// ctrl[0] slot cursor, ctrl[1] live count, ctrl[2] slots in use
+__global__ void flipKernel(unsigned int *ctrl, int compact) {
+  ctrl[0] = 0u;
+  if (compact)
+    ctrl[2] = ctrl[1];
+  ctrl[1] = 0u;
+}
+cudaError_t launchFlip(unsigned int *ctrl, int compact, cudaStream_t s) {
+  flipKernel<<<1, 1, 0, s>>>(ctrl, compact);
+  return cudaGetLastError();
 }
 
 cudaError_t launchShade(const TraceParams &p, cudaStream_t s) {
