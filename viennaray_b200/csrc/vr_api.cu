@@ -31,7 +31,7 @@ struct vr_ctx {
   int D = 3;
 
   // device scene (internal = BVH order)
-  float4 *dA = nullptr, *dB = nullptr, *dC = nullptr, *dN = nullptr;
+  float4 *dPrim = nullptr;
   uint32_t *dNbOff = nullptr, *dNbIdx = nullptr;
   Bvh bvh;
   DeviceScene scene{};
@@ -77,13 +77,10 @@ static int failCuda(vr_ctx *ctx, cudaError_t e, const char *what) {
   } while (0)
 
 static void freeDeviceScene(vr_ctx *c) {
-  cudaFree(c->dA);
-  cudaFree(c->dB);
-  cudaFree(c->dC);
-  cudaFree(c->dN);
+  cudaFree(c->dPrim);
   cudaFree(c->dNbOff);
   cudaFree(c->dNbIdx);
-  c->dA = c->dB = c->dC = c->dN = nullptr;
+  c->dPrim = nullptr;
   c->dNbOff = c->dNbIdx = nullptr;
   freeBvh(&c->bvh);
   c->committed = false;
@@ -441,18 +438,15 @@ int vr_scene_commit(vr_ctx *ctx) {
   CK(cudaMemcpy(s2o.data(), ctx->bvh.sortedToOrig, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
   for (uint32_t i = 0; i < n; ++i)
     o2s[s2o[i]] = i;
-  std::vector<float4> sA(n), sB(n), sC, sN;
-  if (tri) {
-    sC.resize(n);
-    sN.resize(n);
-  }
+  const size_t per = tri ? 4 : 2;  // float4 records per primitive
+  std::vector<float4> sPrim(per * n);
   for (uint32_t i = 0; i < n; ++i) {
     uint32_t o = s2o[i];
-    sA[i] = ctx->hA[o];
-    sB[i] = ctx->hB[o];
+    sPrim[per * i] = ctx->hA[o];
+    sPrim[per * i + 1] = ctx->hB[o];
     if (tri) {
-      sC[i] = ctx->hC[o];
-      sN[i] = ctx->hN[o];
+      sPrim[per * i + 2] = ctx->hC[o];
+      sPrim[per * i + 3] = ctx->hN[o];
     }
   }
   std::vector<uint32_t> off(n + 1, 0u), idx(ctx->hNbIdx.size());
@@ -465,16 +459,8 @@ int vr_scene_commit(vr_ctx *ctx) {
     for (uint32_t k = ctx->hNbOff[o]; k < ctx->hNbOff[o + 1]; ++k)
       idx[w++] = o2s[ctx->hNbIdx[k]];
   }
-  CK(cudaMalloc(&ctx->dA, bytes));
-  CK(cudaMalloc(&ctx->dB, bytes));
-  CK(cudaMemcpy(ctx->dA, sA.data(), bytes, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->dB, sB.data(), bytes, cudaMemcpyHostToDevice));
-  if (tri) {
-    CK(cudaMalloc(&ctx->dC, bytes));
-    CK(cudaMalloc(&ctx->dN, bytes));
-    CK(cudaMemcpy(ctx->dC, sC.data(), bytes, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->dN, sN.data(), bytes, cudaMemcpyHostToDevice));
-  }
+  CK(cudaMalloc(&ctx->dPrim, sizeof(float4) * per * n));
+  CK(cudaMemcpy(ctx->dPrim, sPrim.data(), sizeof(float4) * per * n, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&ctx->dNbOff, sizeof(uint32_t) * (n + 1)));
   CK(cudaMalloc(&ctx->dNbIdx, sizeof(uint32_t) * std::max<size_t>(idx.size(), 1)));
   CK(cudaMemcpy(ctx->dNbOff, off.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice));
@@ -484,10 +470,11 @@ int vr_scene_commit(vr_ctx *ctx) {
   DeviceScene &s = ctx->scene;
   s.geoType = ctx->geoType;
   s.numPrims = n;
-  s.primA = ctx->dA;
-  s.primB = ctx->dB;
-  s.primC = ctx->dC;
-  s.primN = tri ? ctx->dN : ctx->dB;
+  s.prim = ctx->dPrim;
+  for (int a = 0; a < 3; ++a) {
+    s.qLo[a] = ctx->bvh.qLo[a];
+    s.qScale[a] = ctx->bvh.qScale[a];
+  }
   s.nbOff = ctx->dNbOff;
   s.nbIdx = ctx->dNbIdx;
   s.nodes = ctx->bvh.nodes;

@@ -6,7 +6,7 @@
 //   3. Karras-2012 binary radix tree over the sorted codes, one thread per
 //      internal node; index bits break ties between equal codes
 //   4. bottom-up refit of node boxes with one atomic flag per node
-//   5. emission of 64-byte nodes holding both child boxes; subtrees of at
+//   5. emission of 32-byte nodes holding both child boxes on a 16-bit grid; subtrees of at
 //      most VR_LEAF_MAX primitives become leaves (contiguous sorted ranges)
 #include <cub/device/device_radix_sort.cuh>
 
@@ -137,9 +137,27 @@ __device__ __forceinline__ uint32_t childRef(int first, int last, int internalId
   return (uint32_t)internalIdx;
 }
 
+// box -> six 16-bit grid coordinates, rounded outwards by one extra cell so the
+// decode (a fused multiply-add in the traversal) can never shrink the box
+__device__ __forceinline__ uint4 quantizeChild(float4 l, float4 h, float3 qLo, float3 qInv,
+                                               uint32_t ref) {
+  auto qdn = [](float v, float o, float inv) -> uint32_t {
+    float q = floorf((v - o) * inv) - 1.f;
+    return (uint32_t)fminf(fmaxf(q, 0.f), 65535.f);
+  };
+  auto qup = [](float v, float o, float inv) -> uint32_t {
+    float q = ceilf((v - o) * inv) + 1.f;
+    return (uint32_t)fminf(fmaxf(q, 0.f), 65535.f);
+  };
+  uint32_t lx = qdn(l.x, qLo.x, qInv.x), ly = qdn(l.y, qLo.y, qInv.y), lz = qdn(l.z, qLo.z, qInv.z);
+  uint32_t hx = qup(h.x, qLo.x, qInv.x), hy = qup(h.y, qLo.y, qInv.y), hz = qup(h.z, qLo.z, qInv.z);
+  return make_uint4(lx | (ly << 16), lz | (hx << 16), hy | (hz << 16), ref);
+}
+
 __global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
                            const int2 *range, const int *split, const float4 *nodeLo,
-                           const float4 *nodeHi, Node2 *nodes, unsigned int *stats) {
+                           const float4 *nodeHi, Node2 *nodes, unsigned int *stats, float3 qLo,
+                           float3 qInv) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1)
     return;
@@ -172,10 +190,8 @@ __global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *s
     ref1 = childRef(rc.x, rc.y, g + 1);
   }
   Node2 nd;
-  nd.a = make_float4(l0.x, l0.y, l0.z, h0.x);
-  nd.b = make_float4(h0.y, h0.z, l1.x, l1.y);
-  nd.c = make_float4(l1.z, h1.x, h1.y, h1.z);
-  nd.d = make_float4(__uint_as_float(ref0), __uint_as_float(ref1), 0.f, 0.f);
+  nd.c0 = quantizeChild(l0, h0, qLo, qInv, ref0);
+  nd.c1 = quantizeChild(l1, h1, qLo, qInv, ref1);
   nodes[i] = nd;
   atomicAdd(&stats[0], 1u);
   unsigned leaves = ((ref0 & VR_LEAF_FLAG) ? 1u : 0u) + ((ref1 & VR_LEAF_FLAG) ? 1u : 0u);
@@ -238,6 +254,22 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
   VR_CK(cudaMalloc(&keysSorted, sizeof(unsigned long long) * n));
   VR_CK(cudaMalloc(&vals, sizeof(uint32_t) * n));
   VR_CK(cudaMalloc(&out->sortedToOrig, sizeof(uint32_t) * n));
+  // quantisation grid of the node boxes: 65536 cells over the (padded) scene box
+  float3 qLo, qInv;
+  {
+    float ql[3], qi[3];
+    for (int a = 0; a < 3; ++a) {
+      float ext = sceneHi[a] - sceneLo[a];
+      float margin = 1e-3f * ext + 1e-3f;
+      ql[a] = sceneLo[a] - margin;
+      float sc = (ext + 2.f * margin) / 65535.f;
+      out->qLo[a] = ql[a];
+      out->qScale[a] = sc;
+      qi[a] = 1.f / sc;
+    }
+    qLo = make_float3(ql[0], ql[1], ql[2]);
+    qInv = make_float3(qi[0], qi[1], qi[2]);
+  }
   float3 sLo = make_float3(sceneLo[0], sceneLo[1], sceneLo[2]);
   float3 sInv;
   sInv.x = sceneHi[0] > sceneLo[0] ? 1.f / (sceneHi[0] - sceneLo[0]) : 0.f;
@@ -278,7 +310,7 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
     VR_CK(cudaGetLastError());
     emitKernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(primLo, primHi, out->sortedToOrig, (int)n,
                                                       range, split, nodeLo, nodeHi, out->nodes,
-                                                      stats);
+                                                      stats, qLo, qInv);
     VR_CK(cudaGetLastError());
     unsigned int hs[4];
     VR_CK(cudaMemcpyAsync(hs, stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));

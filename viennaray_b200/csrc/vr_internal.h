@@ -14,26 +14,28 @@
 
 namespace vr {
 
-// Binary BVH node, 64 bytes: the boxes of both children and their references.
-//   a = (lo0.x, lo0.y, lo0.z, hi0.x)   b = (hi0.y, hi0.z, lo1.x, lo1.y)
-//   c = (lo1.z, hi1.x, hi1.y, hi1.z)   d = (ref0, ref1, -, -) as bit patterns
+// Compressed binary BVH node, 32 bytes = one L2 sector: per child a box of six
+// 16-bit coordinates on the scene's quantisation grid (rounded outwards) and a
+// 32-bit reference.
+//   c.x = lo.x | lo.y << 16   c.y = lo.z | hi.x << 16   c.z = hi.y | hi.z << 16
+//   c.w = reference (inner node index, or VR_LEAF_FLAG | first << 4 | count)
 struct alignas(16) Node2 {
-  float4 a, b, c, d;
+  uint4 c0, c1;
 };
 
 struct DeviceScene {
   int D;
   int geoType;  // 0 disk, 1 triangle
   uint32_t numPrims;
-  // primitives in BVH (Morton) order -- the INTERNAL primitive index
-  const float4 *primA;  // disk: x,y,z,r        triangle: v0 (w = original ID)
-  const float4 *primB;  // disk: nx,ny,nz,orig  triangle: v1
-  const float4 *primC;  //                      triangle: v2
-  const float4 *primN;  // disk: = primB        triangle: nx,ny,nz,orig
+  // primitives in BVH (Morton) order -- the INTERNAL primitive index.
+  // disk i:     prim[2i] = x,y,z,r   prim[2i+1] = nx,ny,nz,original ID  (one sector)
+  // triangle i: prim[4i..4i+2] = v0,v1,v2 (w = original ID)  prim[4i+3] = normal
+  const float4 *prim;
   const uint32_t *nbOff;  // neighbour CSR, internal indices
   const uint32_t *nbIdx;
   const Node2 *nodes;
   uint32_t rootRef;
+  float qLo[3], qScale[3];  // node box coordinate = qLo + q * qScale
   // boundary (rayBoundary.hpp:164-245)
   float bbox[2][3];
   int firstDir, secondDir;
@@ -82,6 +84,7 @@ struct Bvh {
   uint32_t numNodes = 0;
   uint32_t rootRef = 0;
   uint32_t *sortedToOrig = nullptr;  // device, numPrims
+  float qLo[3] = {0, 0, 0}, qScale[3] = {1, 1, 1};
   float buildMs = 0.f;
   uint32_t numLeaves = 0, maxLeaf = 0;
 };

@@ -116,9 +116,13 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
             ix = 1.f / (fabsf(dir.x) > 1e-20f ? dir.x : copysignf(1e-20f, dir.x));
             iy = 1.f / (fabsf(dir.y) > 1e-20f ? dir.y : copysignf(1e-20f, dir.y));
             iz = 1.f / (fabsf(dir.z) > 1e-20f ? dir.z : copysignf(1e-20f, dir.z));
-            ox = -org.x * ix;
-            oy = -org.y * iy;
-            oz = -org.z * iz;
+            // node boxes live on the 16-bit grid: t = q * (scale/d) + (qLo - org)/d
+            ox = (sc.qLo[0] - org.x) * ix;
+            oy = (sc.qLo[1] - org.y) * iy;
+            oz = (sc.qLo[2] - org.z) * iz;
+            ix *= sc.qScale[0];
+            iy *= sc.qScale[1];
+            iz *= sc.qScale[2];
             // the shade / init kernel already intersected the boundary box
             const float4 h0 = __ldcs(&p.pool.hit[s]);
             best.t = h0.x;
@@ -139,28 +143,34 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
     // ---- inner nodes ----------------------------------------------------------
     while (cur < VR_DONE) {  // neither leaf (bit 31) nor DONE
       const Node2 *n = sc.nodes + cur;
-      const float4 a = __ldg(&n->a), b = __ldg(&n->b), c = __ldg(&n->c), d = __ldg(&n->d);
+      const uint4 c0 = __ldg(&n->c0), c1 = __ldg(&n->c1);
       ++wNodes;
-      // slab test t = lo * (1/d) - org/d with an explicit FMA; boxes were
-      // padded at build time and the comparison is widened, so rounding here
-      // can only add visits.  NaN (0 * inf) drops out of fminf / fmaxf.
-      const float t0x = __fmaf_rn(a.x, ix, ox), t1x = __fmaf_rn(a.w, ix, ox);
-      const float t0y = __fmaf_rn(a.y, iy, oy), t1y = __fmaf_rn(b.x, iy, oy);
-      const float t0z = __fmaf_rn(a.z, iz, oz), t1z = __fmaf_rn(b.y, iz, oz);
+      // slab tests with an explicit FMA per plane; the boxes were rounded
+      // outwards by a full grid cell at build time and the comparison is
+      // widened, so rounding here can only add visits
+      const float t0x = __fmaf_rn((float)(c0.x & 0xffffu), ix, ox),
+                  t1x = __fmaf_rn((float)(c0.y >> 16), ix, ox);
+      const float t0y = __fmaf_rn((float)(c0.x >> 16), iy, oy),
+                  t1y = __fmaf_rn((float)(c0.z & 0xffffu), iy, oy);
+      const float t0z = __fmaf_rn((float)(c0.y & 0xffffu), iz, oz),
+                  t1z = __fmaf_rn((float)(c0.z >> 16), iz, oz);
       const float n0 =
           fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
       const float f0 =
           fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
-      const float u0x = __fmaf_rn(b.z, ix, ox), u1x = __fmaf_rn(c.y, ix, ox);
-      const float u0y = __fmaf_rn(b.w, iy, oy), u1y = __fmaf_rn(c.z, iy, oy);
-      const float u0z = __fmaf_rn(c.x, iz, oz), u1z = __fmaf_rn(c.w, iz, oz);
+      const float u0x = __fmaf_rn((float)(c1.x & 0xffffu), ix, ox),
+                  u1x = __fmaf_rn((float)(c1.y >> 16), ix, ox);
+      const float u0y = __fmaf_rn((float)(c1.x >> 16), iy, oy),
+                  u1y = __fmaf_rn((float)(c1.z & 0xffffu), iy, oy);
+      const float u0z = __fmaf_rn((float)(c1.y & 0xffffu), iz, oz),
+                  u1z = __fmaf_rn((float)(c1.z >> 16), iz, oz);
       const float n1 =
           fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), VR_TNEAR));
       const float f1 =
           fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), best.t));
       const bool h0 = n0 * 0.99999f <= f0 * 1.00001f + 1e-6f;
       const bool h1 = n1 * 0.99999f <= f1 * 1.00001f + 1e-6f;
-      const uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
+      const uint32_t r0 = c0.w, r1 = c1.w;
       if (h0 && h1) {
         const bool swap = n1 < n0;
         if (sp < VR_STACK)
@@ -181,11 +191,12 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
       for (uint32_t k = 0; k < count; ++k) {
         const uint32_t i = first + k;
         if (GEO == 0) {
-          const float4 P = __ldg(&sc.primA[i]);
-          const float4 N = __ldg(&sc.primB[i]);
+          const float4 P = __ldg(&sc.prim[2 * i]);
+          const float4 N = __ldg(&sc.prim[2 * i + 1]);
           testDisk(P, N, i, org, dir, best);
         } else {
-          const float4 a = __ldg(&sc.primA[i]), b = __ldg(&sc.primB[i]), c = __ldg(&sc.primC[i]);
+          const float4 a = __ldg(&sc.prim[4 * i]), b = __ldg(&sc.prim[4 * i + 1]),
+                       c = __ldg(&sc.prim[4 * i + 2]);
           testTri({a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, 1u, i, __float_as_uint(a.w),
                   org, dir, best, nullptr);
         }
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ Trace
       }
     } else {
       const V3 hitPoint = {org.x + dir.x * ht, org.y + dir.y * ht, org.z + dir.z * ht};
-      const float4 N4 = __ldg(&sc.primN[hprim]);
+      const float4 N4 = __ldg(&sc.prim[GEO == 0 ? 2 * hprim + 1 : 4 * hprim + 3]);
       const V3 gn = {N4.x, N4.y, N4.z};
       const bool backface = dot(rayDirection, gn) > 0.f;  // :224
       if (backface) {
@@ -439,15 +450,29 @@ __global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ Trace
         ++wFlux;
         if (GEO == 0) {  // :271-280 neighbour spread
           const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
-          for (uint32_t k = k0; k < k1; ++k) {
-            const uint32_t id = __ldg(&sc.nbIdx[k]);
-            const float4 P = __ldg(&sc.primA[id]);
-            const float4 Nn = __ldg(&sc.primB[id]);
-            ++wNb;
-            if (checkLocal(P, Nn, org, dir)) {
-              atomicAdd(&p.flux[id], wf);
-              ++wFlux;
-            }
+          // four neighbours per round: all index loads, then all disk loads,
+          // then the tests, so the gathers overlap
+          for (uint32_t k = k0; k < k1; k += 4) {
+            uint32_t id[4];
+            float4 P[4], Nn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (id[j] != VR_INVALID_ID) {
+                P[j] = __ldg(&sc.prim[2 * id[j]]);
+                Nn[j] = __ldg(&sc.prim[2 * id[j] + 1]);
+              }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (id[j] != VR_INVALID_ID) {
+                ++wNb;
+                if (checkLocal(P[j], Nn[j], org, dir)) {
+                  atomicAdd(&p.flux[id[j]], wf);
+                  ++wFlux;
+                }
+              }
           }
         }
         rng.load(p.pool.rng[s], p.seed, p.stream, idx);
@@ -708,7 +733,7 @@ __global__ void debugReadHitsKernel(DeviceScene sc, RayPool pool, uint32_t m, ui
       uint32_t k0 = sc.nbOff[hprim], k1 = sc.nbOff[hprim + 1];
       for (uint32_t k = k0; k < k1; ++k) {
         uint32_t id = sc.nbIdx[k];
-        if (checkLocal(sc.primA[id], sc.primB[id], org, dir)) {
+        if (checkLocal(sc.prim[2 * id], sc.prim[2 * id + 1], org, dir)) {
           if (cnt < nbCap)
             nbOut[(size_t)i * nbCap + cnt] = sortedToOrig[id];
           ++cnt;
