@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libviennaray_b200.so")
+LIB_PATH = os.environ.get("VR_LIB_PATH") or os.path.join(_HERE, "libviennaray_b200.so")
 
 _vp = C.c_void_p
 FLUX_FIXED_SCALE = float(2**30)

@@ -19,6 +19,9 @@
 namespace vr {
 
 #define VR_STACK 96
+#ifndef VR_PEND
+#define VR_PEND 0  // leaves a lane may postpone while it keeps traversing (measured: 0 is fastest)
+#endif
 #define VR_DONE 0x7fffffffu  // traversal finished (not a valid node index)
 
 __device__ __forceinline__ bool slotEmpty(const float4 &od0) { return od0.w != od0.w; }
@@ -30,6 +33,9 @@ __device__ __forceinline__ bool slotEmpty(const float4 &od0) { return od0.w != o
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void boundaryTest(const DeviceScene &sc, const V3 &org, const V3 &dir,
                                              Hit &best) {
+  // margin of the cheap rectangle check, in length units
+  const float ext = fmaxf(fmaxf(sc.bbox[1][0] - sc.bbox[0][0], sc.bbox[1][1] - sc.bbox[0][1]),
+                          sc.bbox[1][2] - sc.bbox[0][2]);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int axis = k < 2 ? sc.firstDir : sc.secondDir;
@@ -39,6 +45,14 @@ __device__ __forceinline__ void boundaryTest(const DeviceScene &sc, const V3 &or
       continue;
     const float tp = (c - comp(org, axis)) / da;
     if (!(tp >= 0.5f * VR_TNEAR && tp <= best.t * 1.00001f + 1e-5f))
+      continue;
+    // the plane's two triangles tile the box face: skip them when the plane
+    // point is clearly outside that rectangle
+    const float m = 1e-4f * (ext + fabsf(tp));
+    const float hx = org.x + dir.x * tp, hy = org.y + dir.y * tp, hz = org.z + dir.z * tp;
+    if ((axis != 0 && (hx < sc.bbox[0][0] - m || hx > sc.bbox[1][0] + m)) ||
+        (axis != 1 && (hy < sc.bbox[0][1] - m || hy > sc.bbox[1][1] + m)) ||
+        (axis != 2 && (hz < sc.bbox[0][2] - m || hz > sc.bbox[1][2] + m)))
       continue;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -87,6 +101,8 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
   uint32_t cur = VR_DONE;
   uint32_t stack[VR_STACK];
   int sp = 0;
+  uint32_t pend[VR_PEND > 0 ? VR_PEND : 1];
+  int npend = 0;
   bool exhausted = false;
   unsigned wNodes = 0, wPrims = 0;
 
@@ -140,70 +156,90 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
       continue;
     }
 
-    // ---- inner nodes ----------------------------------------------------------
-    while (cur < VR_DONE) {  // neither leaf (bit 31) nor DONE
-      const Node2 *n = sc.nodes + cur;
-      const uint4 c0 = __ldg(&n->c0), c1 = __ldg(&n->c1);
-      ++wNodes;
-      // slab tests with an explicit FMA per plane; the boxes were rounded
-      // outwards by a full grid cell at build time and the comparison is
-      // widened, so rounding here can only add visits
-      const float t0x = __fmaf_rn((float)(c0.x & 0xffffu), ix, ox),
-                  t1x = __fmaf_rn((float)(c0.y >> 16), ix, ox);
-      const float t0y = __fmaf_rn((float)(c0.x >> 16), iy, oy),
-                  t1y = __fmaf_rn((float)(c0.z & 0xffffu), iy, oy);
-      const float t0z = __fmaf_rn((float)(c0.y & 0xffffu), iz, oz),
-                  t1z = __fmaf_rn((float)(c0.z >> 16), iz, oz);
-      const float n0 =
-          fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
-      const float f0 =
-          fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
-      const float u0x = __fmaf_rn((float)(c1.x & 0xffffu), ix, ox),
-                  u1x = __fmaf_rn((float)(c1.y >> 16), ix, ox);
-      const float u0y = __fmaf_rn((float)(c1.x >> 16), iy, oy),
-                  u1y = __fmaf_rn((float)(c1.z & 0xffffu), iy, oy);
-      const float u0z = __fmaf_rn((float)(c1.y & 0xffffu), iz, oz),
-                  u1z = __fmaf_rn((float)(c1.z >> 16), iz, oz);
-      const float n1 =
-          fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), VR_TNEAR));
-      const float f1 =
-          fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), best.t));
-      const bool h0 = n0 * 0.99999f <= f0 * 1.00001f + 1e-6f;
-      const bool h1 = n1 * 0.99999f <= f1 * 1.00001f + 1e-6f;
-      const uint32_t r0 = c0.w, r1 = c1.w;
-      if (h0 && h1) {
-        const bool swap = n1 < n0;
-        if (sp < VR_STACK)
-          stack[sp++] = swap ? r0 : r1;
-        cur = swap ? r1 : r0;
-      } else if (h0) {
-        cur = r0;
-      } else if (h1) {
-        cur = r1;
-      } else {
+    // ---- inner nodes; a leaf that is reached is postponed (up to VR_PEND of
+    // them) and the traversal goes on speculatively, so that the lanes of the
+    // warp stay in this loop together for longer -------------------------------
+    for (;;) {
+      if (cur < VR_DONE) {  // inner node
+        const Node2 *n = sc.nodes + cur;
+        const uint4 c0 = __ldg(&n->c0), c1 = __ldg(&n->c1);
+        ++wNodes;
+        // slab tests with an explicit FMA per plane; the boxes were rounded
+        // outwards by a full grid cell at build time and the comparison is
+        // widened, so rounding here can only add visits
+        const float t0x = __fmaf_rn((float)(c0.x & 0xffffu), ix, ox),
+                    t1x = __fmaf_rn((float)(c0.y >> 16), ix, ox);
+        const float t0y = __fmaf_rn((float)(c0.x >> 16), iy, oy),
+                    t1y = __fmaf_rn((float)(c0.z & 0xffffu), iy, oy);
+        const float t0z = __fmaf_rn((float)(c0.y & 0xffffu), iz, oz),
+                    t1z = __fmaf_rn((float)(c0.z >> 16), iz, oz);
+        const float n0 =
+            fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
+        const float f0 =
+            fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
+        const float u0x = __fmaf_rn((float)(c1.x & 0xffffu), ix, ox),
+                    u1x = __fmaf_rn((float)(c1.y >> 16), ix, ox);
+        const float u0y = __fmaf_rn((float)(c1.x >> 16), iy, oy),
+                    u1y = __fmaf_rn((float)(c1.z & 0xffffu), iy, oy);
+        const float u0z = __fmaf_rn((float)(c1.y & 0xffffu), iz, oz),
+                    u1z = __fmaf_rn((float)(c1.z >> 16), iz, oz);
+        const float n1 =
+            fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), VR_TNEAR));
+        const float f1 =
+            fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), best.t));
+        const bool h0 = n0 * 0.99999f <= f0 * 1.00001f + 1e-6f;
+        const bool h1 = n1 * 0.99999f <= f1 * 1.00001f + 1e-6f;
+        const uint32_t r0 = c0.w, r1 = c1.w;
+        if (h0 && h1) {
+          const bool swap = n1 < n0;
+          if (sp < VR_STACK)
+            stack[sp++] = swap ? r0 : r1;
+          cur = swap ? r1 : r0;
+        } else if (h0) {
+          cur = r0;
+        } else if (h1) {
+          cur = r1;
+        } else {
+          cur = sp ? stack[--sp] : VR_DONE;
+        }
+      } else if (cur != VR_DONE && npend < VR_PEND) {  // leaf: postpone it
+        pend[npend++] = cur;
         cur = sp ? stack[--sp] : VR_DONE;
+      } else {
+        break;
       }
     }
 
-    // ---- leaf ---------------------------------------------------------------------
-    if (cur & VR_LEAF_FLAG) {
-      const uint32_t first = (cur & 0x7fffffffu) >> 4, count = cur & 15u;
-      for (uint32_t k = 0; k < count; ++k) {
-        const uint32_t i = first + k;
-        if (GEO == 0) {
-          const float4 P = __ldg(&sc.prim[2 * i]);
-          const float4 N = __ldg(&sc.prim[2 * i + 1]);
-          testDisk(P, N, i, org, dir, best);
-        } else {
-          const float4 a = __ldg(&sc.prim[4 * i]), b = __ldg(&sc.prim[4 * i + 1]),
-                       c = __ldg(&sc.prim[4 * i + 2]);
-          testTri({a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, 1u, i, __float_as_uint(a.w),
-                  org, dir, best, nullptr);
-        }
+    // ---- leaves: the postponed ones, then the one the lane stopped at -------------
+#pragma unroll
+    for (int q = 0; q <= VR_PEND; ++q) {
+      uint32_t ref = 0u;
+      if (q < VR_PEND) {
+        if (q < npend)
+          ref = pend[q];
+      } else if (cur & VR_LEAF_FLAG) {
+        ref = cur;
+        cur = sp ? stack[--sp] : VR_DONE;
       }
-      wPrims += count;
-      cur = sp ? stack[--sp] : VR_DONE;
+      if (ref) {
+        const uint32_t first = (ref & 0x7fffffffu) >> 4, count = ref & 15u;
+        for (uint32_t k = 0; k < count; ++k) {
+          const uint32_t i = first + k;
+          if (GEO == 0) {
+            const float4 P = __ldg(&sc.prim[2 * i]);
+            const float4 N = __ldg(&sc.prim[2 * i + 1]);
+            testDisk(P, N, i, org, dir, best);
+          } else {
+            const float4 a = __ldg(&sc.prim[4 * i]), b = __ldg(&sc.prim[4 * i + 1]),
+                         c = __ldg(&sc.prim[4 * i + 2]);
+            testTri({a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, 1u, i,
+                    __float_as_uint(a.w), org, dir, best, nullptr);
+          }
+        }
+        wPrims += count;
+      }
     }
+    npend = 0;
 
     // ---- finished: publish the hit, free the lane ---------------------------------
     if (slot != VR_INVALID_ID && cur == VR_DONE) {
