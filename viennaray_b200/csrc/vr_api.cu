@@ -54,7 +54,7 @@ struct vr_ctx {
   int kernelLaunches = 0;
   int iterations = 0;
   bool countWork = false;
-  uint32_t poolSlots = 1u << 22;
+  uint32_t poolSlots = 1u << 24;
 };
 
 static std::string g_createError;
@@ -189,7 +189,7 @@ int vr_ctx_create(int cudaDevice, vr_ctx **out) {
       (e = cudaMalloc(&ctx->dSlotCursor, 4 * sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaMalloc(&ctx->dCounterCopies,
                       VR_COUNTER_COPIES * 8 * sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMallocHost(&ctx->hLive, 4 * sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaMallocHost(&ctx->hLive, 8 * sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->liveEv[0], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->liveEv[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->liveEv[2], cudaEventDisableTiming)) != cudaSuccess ||
@@ -568,41 +568,54 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
     CK(launchInitPool(p, ctx->stream));
     CK(launchFlip(ctx->dSlotCursor, 0, ctx->stream));
     ctx->kernelLaunches += 2;
-    // Wavefront iterations.  The live count of iteration i is read back two
-    // iterations later so the device never waits for the host.  Once a count
+    // Wavefront iterations, launched in batches with one read-back (survivor
+    // count, ray cursor) per batch.  While the source still has rays every slot
+    // stays alive, and an iteration hands out at most `slots` new rays, so
+    // remaining / slots iterations can be queued blind.  Once a survivor count
     // below the pool size shows that the source is exhausted, the shade kernel
     // compacts the survivors into the other pool and the launches shrink.
     bool compact = false, compacted = false;
-    uint32_t bound = slots;  // upper bound of the survivors (lagging read-back)
+    uint32_t bound = slots;  // upper bound of the survivors (from the last read-back)
+    uint64_t handed = std::min<uint64_t>(slots, shardRays);
     int cur = 0;
-    for (int it = 0;; ++it) {
-      p.pool = cur ? ctx->pool2 : ctx->pool;
-      p.poolOut = cur ? ctx->pool : ctx->pool2;
-      p.compact = compact ? 1 : 0;
-      p.numSlots = compacted ? bound : slots;  // the first compacting pass reads every slot
-      CK(launchTraverse(p, ctx->numSMs, ctx->stream));
-      CK(launchShade(p, ctx->stream));
-      const int r = it & 3;
-      CK(cudaMemcpyAsync(&ctx->hLive[r], p.liveCount, sizeof(unsigned int),
-                         cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaEventRecord(ctx->liveEv[r], ctx->stream));
-      CK(launchFlip(ctx->dSlotCursor, p.compact, ctx->stream));
-      ctx->kernelLaunches += 3;
-      ++ctx->iterations;
-      if (compact) {
-        cur ^= 1;
-        compacted = true;
-      }
-      if (it >= 2) {
-        const int q = (it - 2) & 3;
-        CK(cudaEventSynchronize(ctx->liveEv[q]));
-        const uint32_t live = ctx->hLive[q];
-        if (live == 0u)
-          break;
-        if (live < slots) {
-          compact = true;
-          bound = std::min(bound, live);
+    for (;;) {
+      int batch = 1;
+      if (!compact)
+        batch = (int)std::min<uint64_t>(std::max<uint64_t>((shardRays - handed) / slots, 1), 256);
+      else if (compacted)
+        batch = bound > 262144u ? 2 : 16;
+      for (int b = 0; b < batch; ++b) {
+        p.pool = cur ? ctx->pool2 : ctx->pool;
+        p.poolOut = cur ? ctx->pool : ctx->pool2;
+        p.compact = compact ? 1 : 0;
+        p.numSlots = compacted ? bound : slots;  // the first compacting pass reads every slot
+        CK(launchTraverse(p, ctx->numSMs, ctx->stream));
+        CK(launchShade(p, ctx->stream));
+        if (b == batch - 1) {
+          CK(cudaMemcpyAsync(&ctx->hLive[0], p.liveCount, sizeof(unsigned int),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+          CK(cudaMemcpyAsync(&ctx->hLive[2], ctx->dCursor, sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, ctx->stream));
         }
+        CK(launchFlip(ctx->dSlotCursor, p.compact, ctx->stream));
+        ctx->kernelLaunches += 3;
+        ++ctx->iterations;
+        if (compact) {
+          cur ^= 1;
+          compacted = true;
+        }
+      }
+      CK(cudaEventRecord(ctx->liveEv[0], ctx->stream));
+      CK(cudaEventSynchronize(ctx->liveEv[0]));
+      const uint32_t live = ctx->hLive[0];
+      unsigned long long cursor;
+      memcpy(&cursor, &ctx->hLive[2], sizeof(cursor));
+      handed = std::min<uint64_t>(cursor, shardRays);
+      if (live == 0u)
+        break;
+      if (live < slots) {
+        compact = true;
+        bound = std::min(bound, live);
       }
     }
     reduceCountersKernel<<<1, 32, 0, ctx->stream>>>(ctx->dCounterCopies,
