@@ -174,6 +174,7 @@ def main():
     import torch
     import torch.distributed as dist
     from viennaray_b200 import capi, host
+    from viennaray_b200 import distributed as vdist
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -210,18 +211,17 @@ def main():
         flush.zero_()  # also loads torch's fill kernel outside the timed region
 
     def shard(step, count):
-        begin = (step * world + rank) * rays
+        begin, _ = vdist.step_shard(step, rays, rank, world)
         return host.config(total_rays_job, SEED, begin, begin + count)
 
     def all_reduce_flux():
+        # the path's one exchange step: sum of the fixed-point flux words and counters
         if world == 1:
             return
         ptr, words = ctx.flux_device()
-        iface = {"shape": (words,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-        holder = type("Buf", (), {"__cuda_array_interface__": iface})()
-        t = torch.as_tensor(holder, device="cuda")
+        t = vdist.as_int64_tensor(ptr, words, torch.device("cuda", local_rank))
         with torch.cuda.stream(stream):
-            dist.all_reduce(t)
+            vdist.all_reduce_words(t)
 
     # per-ray work of this workload (same kernel; counters ride in registers)
     os.environ["VR_COUNT_WORK"] = "1"
