@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libviennaray_b200.so")
-SOURCES = ["vr_api.cu", "vr_bvh.cu", "vr_trace.cu"]
+SOURCES = ["vr_api.cu", "vr_bvh.cu", "vr_scene.cu", "vr_trace.cu"]
 HEADERS = ["vr_internal.h", "vr_device.cuh", os.path.join("..", "..", "include", "viennaray_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -4,6 +4,7 @@
 // vr_trace.cu.  No CPU fallback exists: every entry point needs a device.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -20,11 +21,14 @@ struct vr_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
 
-  // host copy of the scene as set by the caller (original primitive order)
+  // the scene as set by the caller, resident on the device in original order
   int geoType = -1;
-  uint32_t n = 0;
-  std::vector<float4> hA, hB, hC, hN;
-  std::vector<uint32_t> hNbOff, hNbIdx;
+  uint32_t n = 0, numVerts = 0;
+  float *dXyzr = nullptr, *dNxyz = nullptr;               // disks: n x 4, n x 3
+  float *dVerts = nullptr, *dTriN = nullptr;              // triangles: V x 3, n x 3
+  uint32_t *dTris = nullptr;                              // n x 3
+  uint32_t *dNbOffO = nullptr, *dNbIdxO = nullptr;        // neighbour CSR, original indices
+  size_t nbTotal = 0;
   std::vector<int32_t> materialIds;
   float geoLo[3] = {0, 0, 0}, geoHi[3] = {0, 0, 0};
   bool boundarySet = false;
@@ -54,6 +58,10 @@ struct vr_ctx {
   int kernelLaunches = 0;
   int iterations = 0;
   bool countWork = false;
+  bool timeKernels = false;  // VR_TIME_KERNELS=1: CUDA events around every launch
+  std::vector<cudaEvent_t> tev;
+  std::vector<int> tevKind;
+  double phaseMs[3] = {0, 0, 0};  // traverse, shade, other
   uint32_t poolSlots = 1u << 24;
 };
 
@@ -77,13 +85,33 @@ static int failCuda(vr_ctx *ctx, cudaError_t e, const char *what) {
   } while (0)
 
 static void freeDeviceScene(vr_ctx *c) {
-  cudaFree(c->dPrim);
-  cudaFree(c->dNbOff);
-  cudaFree(c->dNbIdx);
+  cudaFreeAsync(c->dPrim, c->stream);
+  cudaFreeAsync(c->dNbOff, c->stream);
+  cudaFreeAsync(c->dNbIdx, c->stream);
   c->dPrim = nullptr;
   c->dNbOff = c->dNbIdx = nullptr;
-  freeBvh(&c->bvh);
+  freeBvh(&c->bvh, c->stream);
   c->committed = false;
+}
+static void freeInputs(vr_ctx *c) {
+  cudaFreeAsync(c->dXyzr, c->stream);
+  cudaFreeAsync(c->dNxyz, c->stream);
+  cudaFreeAsync(c->dVerts, c->stream);
+  cudaFreeAsync(c->dTriN, c->stream);
+  cudaFreeAsync(c->dTris, c->stream);
+  cudaFreeAsync(c->dNbOffO, c->stream);
+  cudaFreeAsync(c->dNbIdxO, c->stream);
+  c->dXyzr = c->dNxyz = c->dVerts = c->dTriN = nullptr;
+  c->dTris = c->dNbOffO = c->dNbIdxO = nullptr;
+  c->nbTotal = 0;
+}
+// stream-ordered upload of a caller array into a fresh device buffer
+template <class T>
+static cudaError_t uploadArray(vr_ctx *c, T **dst, const T *src, size_t count) {
+  cudaError_t e = cudaMallocAsync((void **)dst, sizeof(T) * std::max<size_t>(count, 1), c->stream);
+  if (e == cudaSuccess && count)
+    e = cudaMemcpyAsync(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream);
+  return e;
 }
 static void freeResults(vr_ctx *c) {
   cudaFree(c->dResult);
@@ -143,6 +171,32 @@ __global__ void reduceCountersKernel(const unsigned long long *copies, unsigned 
   }
 }
 
+// optional per-phase timing: an event after every launch, classified by kind
+static void mark(vr_ctx *c, int kind) {
+  if (!c->timeKernels)
+    return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, c->stream);
+  c->tev.push_back(e);
+  c->tevKind.push_back(kind);
+}
+static void collectMarks(vr_ctx *c) {
+  if (!c->timeKernels || c->tev.empty())
+    return;
+  cudaEventSynchronize(c->tev.back());
+  c->phaseMs[0] = c->phaseMs[1] = c->phaseMs[2] = 0;
+  for (size_t i = 1; i < c->tev.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->tev[i - 1], c->tev[i]);
+    c->phaseMs[c->tevKind[i]] += ms;
+  }
+  for (auto e : c->tev)
+    cudaEventDestroy(e);
+  c->tev.clear();
+  c->tevKind.clear();
+}
+
 extern "C" {
 
 const char *vr_last_error(const vr_ctx *ctx) {
@@ -172,11 +226,21 @@ int vr_ctx_create(int cudaDevice, vr_ctx **out) {
     return fail(nullptr, VR_ERR_CUDA,
                 "vr_ctx_create: kernels are built for sm_100a only; device is sm_" +
                     std::to_string(prop.major * 10 + prop.minor));
+  {
+    // keep freed stream-ordered allocations cached: scene commits reuse them
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, cudaDevice) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   vr_ctx *ctx = new vr_ctx();
   ctx->device = cudaDevice;
   ctx->numSMs = prop.multiProcessorCount;
   const char *cw = getenv("VR_COUNT_WORK");
   ctx->countWork = cw && cw[0] == '1';
+  const char *tk = getenv("VR_TIME_KERNELS");
+  ctx->timeKernels = tk && tk[0] == '1';
   if (const char *ps = getenv("VR_POOL_SLOTS")) {
     long v = atol(ps);
     if (v >= 1024 && v <= (1l << 26))
@@ -207,7 +271,11 @@ void vr_ctx_destroy(vr_ctx *ctx) {
   if (!ctx)
     return;
   cudaSetDevice(ctx->device);
-  freeDeviceScene(ctx);
+  if (ctx->stream) {
+    freeDeviceScene(ctx);
+    freeInputs(ctx);
+    cudaStreamSynchronize(ctx->stream);
+  }
   freeResults(ctx);
   cudaFree(ctx->dCursor);
   cudaFree(ctx->dSlotCursor);
@@ -257,47 +325,49 @@ int vr_scene_set_disks(vr_ctx *ctx, const float *xyzr, const float *nxyz, uint32
     return fail(ctx, VR_ERR_UNSUPPORTED, "vr_scene_set_disks: more than 2^27 primitives");
   if ((nbOffsets == nullptr) != (nbIndices == nullptr) && nbOffsets && nbOffsets[n] != 0)
     return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_disks: nbOffsets without nbIndices");
-  ctx->committed = false;
-  ctx->geoType = 0;
-  ctx->n = n;
-  ctx->hA.resize(n);
-  ctx->hB.resize(n);
-  ctx->hC.clear();
-  ctx->hN.clear();
-  for (int a = 0; a < 3; ++a) {
-    ctx->geoLo[a] = INFINITY;
-    ctx->geoHi[a] = -INFINITY;
-  }
-  for (uint32_t i = 0; i < n; ++i) {
-    ctx->hA[i] = make_float4(xyzr[4 * i], xyzr[4 * i + 1], xyzr[4 * i + 2], xyzr[4 * i + 3]);
-    float4 nn = make_float4(nxyz[3 * i], nxyz[3 * i + 1], nxyz[3 * i + 2], 0.f);
-    memcpy(&nn.w, &i, 4);  // original primitive ID rides in .w
-    ctx->hB[i] = nn;
-    for (int a = 0; a < 3; ++a) {
-      float r = xyzr[4 * i + 3], v = xyzr[4 * i + a];
-      ctx->geoLo[a] = std::min(ctx->geoLo[a], v - r);
-      ctx->geoHi[a] = std::max(ctx->geoHi[a], v + r);
-    }
-  }
+  size_t total = 0;
   if (nbOffsets) {
-    ctx->hNbOff.assign(nbOffsets, nbOffsets + n + 1);
     if (nbOffsets[0] != 0)
       return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_disks: nbOffsets[0] must be 0");
     for (uint32_t i = 0; i < n; ++i)
       if (nbOffsets[i + 1] < nbOffsets[i])
         return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_disks: nbOffsets not monotone");
-    ctx->hNbIdx.assign(nbIndices, nbIndices + nbOffsets[n]);
-    for (uint32_t v : ctx->hNbIdx)
-      if (v >= n)
+    total = nbOffsets[n];
+    for (size_t k = 0; k < total; ++k)
+      if (nbIndices[k] >= n)
         return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_disks: neighbour index out of range");
-  } else {
-    ctx->hNbOff.assign(n + 1, 0u);
-    ctx->hNbIdx.clear();
+  }
+  CK(cudaSetDevice(ctx->device));
+  ctx->committed = false;
+  freeInputs(ctx);
+  ctx->geoType = 0;
+  ctx->n = n;
+  ctx->numVerts = 0;
+  for (int a = 0; a < 3; ++a) {
+    ctx->geoLo[a] = INFINITY;
+    ctx->geoHi[a] = -INFINITY;
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    const float r = xyzr[4 * i + 3];
+    for (int a = 0; a < 3; ++a) {
+      const float v = xyzr[4 * i + a];
+      ctx->geoLo[a] = std::min(ctx->geoLo[a], v - r);
+      ctx->geoHi[a] = std::max(ctx->geoHi[a], v + r);
+    }
+  }
+  CK(uploadArray(ctx, &ctx->dXyzr, xyzr, (size_t)4 * n));
+  CK(uploadArray(ctx, &ctx->dNxyz, nxyz, (size_t)3 * n));
+  if (nbOffsets) {
+    CK(uploadArray(ctx, &ctx->dNbOffO, nbOffsets, (size_t)n + 1));
+    CK(uploadArray(ctx, &ctx->dNbIdxO, nbIndices, total));
+    ctx->nbTotal = total;
   }
   if (materialIds)
     ctx->materialIds.assign(materialIds, materialIds + n);
   else
     ctx->materialIds.assign(n, 0);
+  // the caller's arrays may be reused as soon as this returns
+  CK(cudaStreamSynchronize(ctx->stream));
   return VR_OK;
 }
 
@@ -309,41 +379,34 @@ int vr_scene_set_triangles(vr_ctx *ctx, const float *verts, uint32_t nVerts, con
     return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_triangles: no geometry was passed");
   if (n >= (1u << 27))
     return fail(ctx, VR_ERR_UNSUPPORTED, "vr_scene_set_triangles: more than 2^27 primitives");
+  for (size_t k = 0; k < (size_t)3 * n; ++k)
+    if (idx[k] >= nVerts)
+      return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_triangles: vertex index out of range");
+  CK(cudaSetDevice(ctx->device));
   ctx->committed = false;
+  freeInputs(ctx);
   ctx->geoType = 1;
   ctx->n = n;
-  ctx->hA.resize(n);
-  ctx->hB.resize(n);
-  ctx->hC.resize(n);
-  ctx->hN.resize(n);
+  ctx->numVerts = nVerts;
   for (int a = 0; a < 3; ++a) {
     ctx->geoLo[a] = INFINITY;
     ctx->geoHi[a] = -INFINITY;
   }
-  for (uint32_t i = 0; i < n; ++i) {
-    float w;
-    memcpy(&w, &i, 4);
-    for (int k = 0; k < 3; ++k) {
-      uint32_t v = idx[3 * i + k];
-      if (v >= nVerts)
-        return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_triangles: vertex index out of range");
-      float4 p = make_float4(verts[3 * v], verts[3 * v + 1], verts[3 * v + 2], w);
-      (k == 0 ? ctx->hA : (k == 1 ? ctx->hB : ctx->hC))[i] = p;
-      ctx->geoLo[0] = std::min(ctx->geoLo[0], p.x);
-      ctx->geoLo[1] = std::min(ctx->geoLo[1], p.y);
-      ctx->geoLo[2] = std::min(ctx->geoLo[2], p.z);
-      ctx->geoHi[0] = std::max(ctx->geoHi[0], p.x);
-      ctx->geoHi[1] = std::max(ctx->geoHi[1], p.y);
-      ctx->geoHi[2] = std::max(ctx->geoHi[2], p.z);
+  for (size_t k = 0; k < (size_t)3 * n; ++k) {  // bounds of the referenced vertices
+    const float *p = verts + 3 * (size_t)idx[k];
+    for (int a = 0; a < 3; ++a) {
+      ctx->geoLo[a] = std::min(ctx->geoLo[a], p[a]);
+      ctx->geoHi[a] = std::max(ctx->geoHi[a], p[a]);
     }
-    ctx->hN[i] = make_float4(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2], w);
   }
-  ctx->hNbOff.assign(n + 1, 0u);
-  ctx->hNbIdx.clear();
+  CK(uploadArray(ctx, &ctx->dVerts, verts, (size_t)3 * nVerts));
+  CK(uploadArray(ctx, &ctx->dTris, idx, (size_t)3 * n));
+  CK(uploadArray(ctx, &ctx->dTriN, normals, (size_t)3 * n));
   if (materialIds)
     ctx->materialIds.assign(materialIds, materialIds + n);
   else
     ctx->materialIds.assign(n, 0);
+  CK(cudaStreamSynchronize(ctx->stream));
   return VR_OK;
 }
 
@@ -388,6 +451,9 @@ int vr_scene_set_boundary(vr_ctx *ctx, const float bboxMin[3], const float bboxM
   return VR_OK;
 }
 
+// Everything below the upload runs on the device: 32-byte primitive records,
+// padded boxes, Morton sort + LBVH, the permutation of the primitives into BVH
+// order and the remapping of the neighbour lists into that index space.
 int vr_scene_commit(vr_ctx *ctx) {
   if (!ctx)
     return VR_ERR_ARGUMENT;
@@ -399,14 +465,19 @@ int vr_scene_commit(vr_ctx *ctx) {
   freeDeviceScene(ctx);
   const uint32_t n = ctx->n;
   const bool tri = ctx->geoType == 1;
-  // 1. original-order primitives to the device, padded boxes, BVH
-  float4 *oA = nullptr, *oB = nullptr, *oC = nullptr, *lo = nullptr, *hi = nullptr;
+  cudaStream_t st = ctx->stream;
+  float4 *A = nullptr, *B = nullptr, *C = nullptr, *N = nullptr, *lo = nullptr, *hi = nullptr;
+  uint32_t *o2s = nullptr, *cnt = nullptr;
   auto tmpFree = [&]() {
-    cudaFree(oA);
-    cudaFree(oB);
-    cudaFree(oC);
-    cudaFree(lo);
-    cudaFree(hi);
+    if (tri)
+      cudaFreeAsync(A, st);  // disks: A aliases the uploaded xyzr rows
+    cudaFreeAsync(B, st);
+    cudaFreeAsync(C, st);
+    cudaFreeAsync(N, st);
+    cudaFreeAsync(lo, st);
+    cudaFreeAsync(hi, st);
+    cudaFreeAsync(o2s, st);
+    cudaFreeAsync(cnt, st);
   };
 #define CKT(call)                                                                                  \
   do {                                                                                             \
@@ -417,56 +488,33 @@ int vr_scene_commit(vr_ctx *ctx) {
     }                                                                                              \
   } while (0)
   const size_t bytes = sizeof(float4) * n;
-  CKT(cudaMalloc(&oA, bytes));
-  CKT(cudaMalloc(&oB, bytes));
-  CKT(cudaMalloc(&lo, bytes));
-  CKT(cudaMalloc(&hi, bytes));
-  CKT(cudaMemcpyAsync(oA, ctx->hA.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CKT(cudaMemcpyAsync(oB, ctx->hB.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CKT(cudaMallocAsync(&B, bytes, st));
+  CKT(cudaMallocAsync(&lo, bytes, st));
+  CKT(cudaMallocAsync(&hi, bytes, st));
   if (tri) {
-    CKT(cudaMalloc(&oC, bytes));
-    CKT(cudaMemcpyAsync(oC, ctx->hC.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CKT(launchTriBounds(oA, oB, oC, n, lo, hi, ctx->stream));
+    CKT(cudaMallocAsync(&A, bytes, st));
+    CKT(cudaMallocAsync(&C, bytes, st));
+    CKT(cudaMallocAsync(&N, bytes, st));
+    CKT(launchPackTriangles(ctx->dVerts, ctx->dTris, ctx->dTriN, n, A, B, C, N, st));
+    CKT(launchTriBounds(A, B, C, n, lo, hi, st));
   } else {
-    CKT(launchDiskBounds(oA, oB, n, lo, hi, ctx->stream));
+    A = reinterpret_cast<float4 *>(ctx->dXyzr);
+    CKT(launchPackDiskNormals(ctx->dNxyz, n, B, st));
+    CKT(launchDiskBounds(A, B, n, lo, hi, st));
   }
-  CKT(buildBvh(lo, hi, n, ctx->geoLo, ctx->geoHi, ctx->stream, &ctx->bvh));
+  CKT(buildBvh(lo, hi, n, ctx->geoLo, ctx->geoHi, st, &ctx->bvh));
+  const size_t per = tri ? 4 : 2;  // float4 records per primitive
+  CKT(cudaMallocAsync(&ctx->dPrim, sizeof(float4) * per * n, st));
+  CKT(launchGatherPrims(ctx->geoType, A, B, C, N, ctx->bvh.sortedToOrig, n, ctx->dPrim, st));
+  CKT(cudaMallocAsync(&ctx->dNbOff, sizeof(uint32_t) * ((size_t)n + 1), st));
+  CKT(cudaMallocAsync(&ctx->dNbIdx, sizeof(uint32_t) * std::max<size_t>(ctx->nbTotal, 1), st));
+  CKT(cudaMallocAsync(&o2s, sizeof(uint32_t) * n, st));
+  CKT(cudaMallocAsync(&cnt, sizeof(uint32_t) * n, st));
+  CKT(remapNeighbors(ctx->bvh.sortedToOrig, ctx->dNbOffO, ctx->dNbIdxO, n, o2s, cnt, ctx->dNbOff,
+                     ctx->dNbIdx, st));
   tmpFree();
 #undef CKT
-  // 2. primitives and neighbour lists in BVH order (internal index space)
-  std::vector<uint32_t> s2o(n), o2s(n);
-  CK(cudaMemcpy(s2o.data(), ctx->bvh.sortedToOrig, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
-  for (uint32_t i = 0; i < n; ++i)
-    o2s[s2o[i]] = i;
-  const size_t per = tri ? 4 : 2;  // float4 records per primitive
-  std::vector<float4> sPrim(per * n);
-  for (uint32_t i = 0; i < n; ++i) {
-    uint32_t o = s2o[i];
-    sPrim[per * i] = ctx->hA[o];
-    sPrim[per * i + 1] = ctx->hB[o];
-    if (tri) {
-      sPrim[per * i + 2] = ctx->hC[o];
-      sPrim[per * i + 3] = ctx->hN[o];
-    }
-  }
-  std::vector<uint32_t> off(n + 1, 0u), idx(ctx->hNbIdx.size());
-  for (uint32_t i = 0; i < n; ++i) {
-    uint32_t o = s2o[i];
-    off[i + 1] = off[i] + (ctx->hNbOff[o + 1] - ctx->hNbOff[o]);
-  }
-  for (uint32_t i = 0; i < n; ++i) {
-    uint32_t o = s2o[i], w = off[i];
-    for (uint32_t k = ctx->hNbOff[o]; k < ctx->hNbOff[o + 1]; ++k)
-      idx[w++] = o2s[ctx->hNbIdx[k]];
-  }
-  CK(cudaMalloc(&ctx->dPrim, sizeof(float4) * per * n));
-  CK(cudaMemcpy(ctx->dPrim, sPrim.data(), sizeof(float4) * per * n, cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&ctx->dNbOff, sizeof(uint32_t) * (n + 1)));
-  CK(cudaMalloc(&ctx->dNbIdx, sizeof(uint32_t) * std::max<size_t>(idx.size(), 1)));
-  CK(cudaMemcpy(ctx->dNbOff, off.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice));
-  if (!idx.empty())
-    CK(cudaMemcpy(ctx->dNbIdx, idx.data(), sizeof(uint32_t) * idx.size(),
-                  cudaMemcpyHostToDevice));
+  CK(cudaStreamSynchronize(st));
   DeviceScene &s = ctx->scene;
   s.geoType = ctx->geoType;
   s.numPrims = n;
@@ -589,8 +637,11 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
         p.poolOut = cur ? ctx->pool : ctx->pool2;
         p.compact = compact ? 1 : 0;
         p.numSlots = compacted ? bound : slots;  // the first compacting pass reads every slot
+        mark(ctx, 2);
         CK(launchTraverse(p, ctx->numSMs, ctx->stream));
+        mark(ctx, 0);
         CK(launchShade(p, ctx->stream));
+        mark(ctx, 1);
         if (b == batch - 1) {
           CK(cudaMemcpyAsync(&ctx->hLive[0], p.liveCount, sizeof(unsigned int),
                              cudaMemcpyDeviceToHost, ctx->stream));
@@ -622,10 +673,16 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
                                                     ctx->dResult + (size_t)np * n + (size_t)k * 8);
     CK(cudaGetLastError());
   }
+  mark(ctx, 2);
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (sync) {
     CK(cudaEventSynchronize(ctx->ev1));
     CK(cudaEventElapsedTime(&ctx->lastMs, ctx->ev0, ctx->ev1));
+  }
+  if (ctx->timeKernels) {
+    collectMarks(ctx);
+    fprintf(stderr, "[vr] phases: traverse %.3f ms, shade %.3f ms, other %.3f ms\n", ctx->phaseMs[0],
+            ctx->phaseMs[1], ctx->phaseMs[2]);
   }
   return VR_OK;
 }
@@ -830,7 +887,9 @@ int vr_debug_intersect(vr_ctx *ctx, const float *rays, uint32_t m, uint32_t *geo
                           ctx->stream));
     }
     CKD(launchDebugLoadRays(ctx->scene, ctx->pool, dRays, m, ctx->stream));
+    CKD(cudaEventRecord(ctx->ev0, ctx->stream));
     CKD(launchTraverse(p, ctx->numSMs, ctx->stream));
+    CKD(cudaEventRecord(ctx->ev1, ctx->stream));
     CKD(launchDebugReadHits(ctx->scene, ctx->pool, m, dGeom, dPrim, dT, wantNb ? nbCap : 0u,
                             wantNb ? dCnt : nullptr, dNb, ctx->bvh.sortedToOrig, ctx->stream));
   }
@@ -844,6 +903,7 @@ int vr_debug_intersect(vr_ctx *ctx, const float *rays, uint32_t m, uint32_t *geo
                         ctx->stream));
   }
   CKD(cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->lastMs, ctx->ev0, ctx->ev1);  // traverse kernel alone
   cleanup();
   return VR_OK;
 }

@@ -216,7 +216,7 @@ __global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *s
 
 cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, const float sceneLo[3],
                      const float sceneHi[3], cudaStream_t stream, Bvh *out) {
-  freeBvh(out);
+  freeBvh(out, stream);
   unsigned long long *keys = nullptr, *keysSorted = nullptr;
   uint32_t *vals = nullptr;
   void *tmp = nullptr;
@@ -226,18 +226,18 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
   unsigned int *stats = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   auto cleanup = [&]() {
-    cudaFree(keys);
-    cudaFree(keysSorted);
-    cudaFree(vals);
-    cudaFree(tmp);
-    cudaFree(range);
-    cudaFree(split);
-    cudaFree(parI);
-    cudaFree(parL);
-    cudaFree(flags);
-    cudaFree(nodeLo);
-    cudaFree(nodeHi);
-    cudaFree(stats);
+    cudaFreeAsync(keys, stream);
+    cudaFreeAsync(keysSorted, stream);
+    cudaFreeAsync(vals, stream);
+    cudaFreeAsync(tmp, stream);
+    cudaFreeAsync(range, stream);
+    cudaFreeAsync(split, stream);
+    cudaFreeAsync(parI, stream);
+    cudaFreeAsync(parL, stream);
+    cudaFreeAsync(flags, stream);
+    cudaFreeAsync(nodeLo, stream);
+    cudaFreeAsync(nodeHi, stream);
+    cudaFreeAsync(stats, stream);
     if (e0)
       cudaEventDestroy(e0);
     if (e1)
@@ -250,10 +250,10 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
   VR_CK(cudaEventCreate(&e0));
   VR_CK(cudaEventCreate(&e1));
   VR_CK(cudaEventRecord(e0, stream));
-  VR_CK(cudaMalloc(&keys, sizeof(unsigned long long) * n));
-  VR_CK(cudaMalloc(&keysSorted, sizeof(unsigned long long) * n));
-  VR_CK(cudaMalloc(&vals, sizeof(uint32_t) * n));
-  VR_CK(cudaMalloc(&out->sortedToOrig, sizeof(uint32_t) * n));
+  VR_CK(cudaMallocAsync(&keys, sizeof(unsigned long long) * n, stream));
+  VR_CK(cudaMallocAsync(&keysSorted, sizeof(unsigned long long) * n, stream));
+  VR_CK(cudaMallocAsync(&vals, sizeof(uint32_t) * n, stream));
+  VR_CK(cudaMallocAsync(&out->sortedToOrig, sizeof(uint32_t) * n, stream));
   // quantisation grid of the node boxes: 65536 cells over the (padded) scene box
   float3 qLo, qInv;
   {
@@ -281,7 +281,7 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
   size_t tmpBytes = 0;
   VR_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, vals,
                                         out->sortedToOrig, (int)n, 0, 63, stream));
-  VR_CK(cudaMalloc(&tmp, tmpBytes ? tmpBytes : 16));
+  VR_CK(cudaMallocAsync(&tmp, tmpBytes ? tmpBytes : 16, stream));
   VR_CK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, out->sortedToOrig,
                                         (int)n, 0, 63, stream));
   if (n <= VR_LEAF_MAX) {
@@ -289,17 +289,17 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
     out->numNodes = 0;
     out->numLeaves = 1;
     out->maxLeaf = n;
-    VR_CK(cudaMalloc(&out->nodes, sizeof(Node2)));
+    VR_CK(cudaMallocAsync(&out->nodes, sizeof(Node2), stream));
   } else {
-    VR_CK(cudaMalloc(&range, sizeof(int2) * (n - 1)));
-    VR_CK(cudaMalloc(&split, sizeof(int) * (n - 1)));
-    VR_CK(cudaMalloc(&parI, sizeof(int) * (n - 1)));
-    VR_CK(cudaMalloc(&parL, sizeof(int) * n));
-    VR_CK(cudaMalloc(&flags, sizeof(int) * (n - 1)));
-    VR_CK(cudaMalloc(&nodeLo, sizeof(float4) * (n - 1)));
-    VR_CK(cudaMalloc(&nodeHi, sizeof(float4) * (n - 1)));
-    VR_CK(cudaMalloc(&stats, sizeof(unsigned int) * 4));
-    VR_CK(cudaMalloc(&out->nodes, sizeof(Node2) * (n - 1)));
+    VR_CK(cudaMallocAsync(&range, sizeof(int2) * (n - 1), stream));
+    VR_CK(cudaMallocAsync(&split, sizeof(int) * (n - 1), stream));
+    VR_CK(cudaMallocAsync(&parI, sizeof(int) * (n - 1), stream));
+    VR_CK(cudaMallocAsync(&parL, sizeof(int) * n, stream));
+    VR_CK(cudaMallocAsync(&flags, sizeof(int) * (n - 1), stream));
+    VR_CK(cudaMallocAsync(&nodeLo, sizeof(float4) * (n - 1), stream));
+    VR_CK(cudaMallocAsync(&nodeHi, sizeof(float4) * (n - 1), stream));
+    VR_CK(cudaMallocAsync(&stats, sizeof(unsigned int) * 4, stream));
+    VR_CK(cudaMallocAsync(&out->nodes, sizeof(Node2) * (n - 1), stream));
     VR_CK(cudaMemsetAsync(flags, 0, sizeof(int) * (n - 1), stream));
     VR_CK(cudaMemsetAsync(stats, 0, sizeof(unsigned int) * 4, stream));
     radixTreeKernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(keysSorted, (int)n, range, split, parI,
@@ -327,9 +327,9 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
   return cudaSuccess;
 }
 
-void freeBvh(Bvh *b) {
-  cudaFree(b->nodes);
-  cudaFree(b->sortedToOrig);
+void freeBvh(Bvh *b, cudaStream_t stream) {
+  cudaFreeAsync(b->nodes, stream);
+  cudaFreeAsync(b->sortedToOrig, stream);
   *b = Bvh();
 }
 

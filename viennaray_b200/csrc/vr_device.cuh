@@ -43,6 +43,21 @@ __device__ __forceinline__ void setComp(V3 &v, int a, float s) {
     v.z = s;
 }
 
+// ---- 256-bit loads (sm_100a LDG.E.256): one L1 wavefront per 32-byte record
+// instead of two 128-bit requests.  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z),
+                 "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z),
+                 "=f"(b.w)
+               : "l"(p));
+}
+
 // ---- Philox4x32-10 keyed on (seed, stream), counter (idx, block) ----------
 __device__ __forceinline__ void philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
                                            uint32_t c2, uint32_t c3, uint32_t out[4]) {

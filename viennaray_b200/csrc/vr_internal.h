@@ -7,7 +7,9 @@
 
 #define VR_INVALID_ID 0xffffffffu
 #define VR_TNEAR 1e-4f            // fillRayPosition default (rayUtil.hpp:218)
-#define VR_LEAF_MAX 4u            // primitives per BVH leaf
+#ifndef VR_LEAF_MAX
+#define VR_LEAF_MAX 4u  // primitives per BVH leaf (<= 15)
+#endif
 #define VR_LEAF_FLAG 0x80000000u  // child reference: leaf(first << 4 | count)
 #define VR_FIXED_SCALE 1073741824.0f
 #define VR_COUNTER_COPIES 16      // replicated TraceInfo counters (summed on download)
@@ -90,7 +92,19 @@ struct Bvh {
 };
 cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, const float sceneLo[3],
                      const float sceneHi[3], cudaStream_t stream, Bvh *out);
-void freeBvh(Bvh *b);
+void freeBvh(Bvh *b, cudaStream_t stream);
+
+// ---- scene preparation (vr_scene.cu) ----------------------------------------
+cudaError_t launchPackDiskNormals(const float *nxyz, uint32_t n, float4 *B, cudaStream_t s);
+cudaError_t launchPackTriangles(const float *verts, const uint32_t *tris, const float *normals,
+                                uint32_t n, float4 *A, float4 *B, float4 *C, float4 *N,
+                                cudaStream_t s);
+cudaError_t launchGatherPrims(int geoType, const float4 *A, const float4 *B, const float4 *C,
+                              const float4 *N, const uint32_t *s2o, uint32_t n, float4 *prim,
+                              cudaStream_t s);
+cudaError_t remapNeighbors(const uint32_t *s2o, const uint32_t *offO, const uint32_t *idxO,
+                           uint32_t n, uint32_t *o2s, uint32_t *cnt, uint32_t *off, uint32_t *idx,
+                           cudaStream_t s);
 
 // ---- kernels (vr_trace.cu) -------------------------------------------------
 cudaError_t launchDiskBounds(const float4 *xyzr, const float4 *nrm, uint32_t n, float4 *lo,

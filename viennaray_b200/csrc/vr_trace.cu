@@ -19,10 +19,19 @@
 namespace vr {
 
 #define VR_STACK 96
-#ifndef VR_PEND
-#define VR_PEND 0  // leaves a lane may postpone while it keeps traversing (measured: 0 is fastest)
+#ifndef VR_NODE_MIN
+#define VR_NODE_MIN 1  // lanes at inner nodes needed to keep the warp in the node loop
 #endif
 #define VR_DONE 0x7fffffffu  // traversal finished (not a valid node index)
+#ifndef VR_REFILL_MIN
+#define VR_REFILL_MIN 1  // idle lanes a warp waits for before it fetches new slots
+#endif
+#ifndef VR_TRAV_BLOCKS
+#define VR_TRAV_BLOCKS 8
+#endif
+#ifndef VR_SHADE_BLOCKS
+#define VR_SHADE_BLOCKS 4
+#endif
 
 __device__ __forceinline__ bool slotEmpty(const float4 &od0) { return od0.w != od0.w; }
 
@@ -86,7 +95,7 @@ __device__ __forceinline__ unsigned long long warpSum(unsigned long long v) {
 // traverse: closest hit of every live slot
 // ---------------------------------------------------------------------------
 template <int GEO>
-__global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(128, VR_TRAV_BLOCKS) traverseKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned ltMask = (1u << lane) - 1u;
@@ -101,15 +110,13 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
   uint32_t cur = VR_DONE;
   uint32_t stack[VR_STACK];
   int sp = 0;
-  uint32_t pend[VR_PEND > 0 ? VR_PEND : 1];
-  int npend = 0;
   bool exhausted = false;
   unsigned wNodes = 0, wPrims = 0;
 
   for (;;) {
     // ---- replace finished lanes from the slot cursor ------------------------
     const unsigned need = __ballot_sync(0xffffffffu, slot == VR_INVALID_ID);
-    if (need && !exhausted) {
+    if (__popc(need) >= VR_REFILL_MIN && !exhausted) {
       const unsigned nNeed = __popc(need);
       const int leader = __ffs(need) - 1;
       unsigned base = 0;
@@ -156,13 +163,24 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
       continue;
     }
 
-    // ---- inner nodes; a leaf that is reached is postponed (up to VR_PEND of
-    // them) and the traversal goes on speculatively, so that the lanes of the
-    // warp stay in this loop together for longer -------------------------------
+    // ---- inner nodes.  The warp stays in this loop while at least VR_NODE_MIN
+    // lanes are at an inner node (or no lane has a leaf to test yet); lanes that
+    // reached a leaf wait here, lanes still at nodes wait during the leaf phase.
     for (;;) {
-      if (cur < VR_DONE) {  // inner node
-        const Node2 *n = sc.nodes + cur;
-        const uint4 c0 = __ldg(&n->c0), c1 = __ldg(&n->c1);
+      const bool atNode = cur < VR_DONE;
+#if VR_NODE_MIN > 1
+      const unsigned nm = __ballot_sync(0xffffffffu, atNode);
+      if (nm == 0u)
+        break;
+      if (__popc(nm) < VR_NODE_MIN && __any_sync(0xffffffffu, cur > VR_DONE))
+        break;
+#else
+      if (!atNode)
+        break;
+#endif
+      if (atNode) {
+        uint4 c0, c1;
+        ldg256(sc.nodes + cur, c0, c1);
         ++wNodes;
         // slab tests with an explicit FMA per plane; the boxes were rounded
         // outwards by a full grid cell at build time and the comparison is
@@ -187,59 +205,45 @@ __global__ void __launch_bounds__(128, 8) traverseKernel(const __grid_constant__
             fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), VR_TNEAR));
         const float f1 =
             fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), best.t));
-        const bool h0 = n0 * 0.99999f <= f0 * 1.00001f + 1e-6f;
-        const bool h1 = n1 * 0.99999f <= f1 * 1.00001f + 1e-6f;
+        const bool h0 = n0 <= __fmaf_rn(f0, 1.00003f, 2e-6f);
+        const bool h1 = n1 <= __fmaf_rn(f1, 1.00003f, 2e-6f);
         const uint32_t r0 = c0.w, r1 = c1.w;
-        if (h0 && h1) {
-          const bool swap = n1 < n0;
-          if (sp < VR_STACK)
-            stack[sp++] = swap ? r0 : r1;
-          cur = swap ? r1 : r0;
-        } else if (h0) {
-          cur = r0;
-        } else if (h1) {
-          cur = r1;
-        } else {
-          cur = sp ? stack[--sp] : VR_DONE;
+        const bool swap = n1 < n0;
+        if (h0 && h1 && sp < VR_STACK) {
+          stack[sp] = swap ? r0 : r1;
+          ++sp;
         }
-      } else if (cur != VR_DONE && npend < VR_PEND) {  // leaf: postpone it
-        pend[npend++] = cur;
-        cur = sp ? stack[--sp] : VR_DONE;
-      } else {
-        break;
+        if (h0 || h1) {
+          cur = (h0 && (!h1 || !swap)) ? r0 : r1;
+        } else {
+          cur = VR_DONE;
+          if (sp)
+            cur = stack[--sp];
+        }
       }
     }
 
-    // ---- leaves: the postponed ones, then the one the lane stopped at -------------
-#pragma unroll
-    for (int q = 0; q <= VR_PEND; ++q) {
-      uint32_t ref = 0u;
-      if (q < VR_PEND) {
-        if (q < npend)
-          ref = pend[q];
-      } else if (cur & VR_LEAF_FLAG) {
-        ref = cur;
-        cur = sp ? stack[--sp] : VR_DONE;
-      }
-      if (ref) {
-        const uint32_t first = (ref & 0x7fffffffu) >> 4, count = ref & 15u;
-        for (uint32_t k = 0; k < count; ++k) {
-          const uint32_t i = first + k;
-          if (GEO == 0) {
-            const float4 P = __ldg(&sc.prim[2 * i]);
-            const float4 N = __ldg(&sc.prim[2 * i + 1]);
-            testDisk(P, N, i, org, dir, best);
-          } else {
-            const float4 a = __ldg(&sc.prim[4 * i]), b = __ldg(&sc.prim[4 * i + 1]),
-                         c = __ldg(&sc.prim[4 * i + 2]);
-            testTri({a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, 1u, i,
-                    __float_as_uint(a.w), org, dir, best, nullptr);
-          }
+    // ---- one leaf per lane that stands at one -----------------------------------
+    if (cur > VR_DONE) {
+      const uint32_t first = (cur & 0x7fffffffu) >> 4, count = cur & 15u;
+      cur = VR_DONE;
+      if (sp)
+        cur = stack[--sp];
+      for (uint32_t k = 0; k < count; ++k) {
+        const uint32_t i = first + k;
+        if (GEO == 0) {
+          float4 P, N;
+          ldg256(&sc.prim[2 * i], P, N);
+          testDisk(P, N, i, org, dir, best);
+        } else {
+          const float4 a = __ldg(&sc.prim[4 * i]), b = __ldg(&sc.prim[4 * i + 1]),
+                       c = __ldg(&sc.prim[4 * i + 2]);
+          testTri({a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, 1u, i, __float_as_uint(a.w),
+                  org, dir, best, nullptr);
         }
-        wPrims += count;
       }
+      wPrims += count;
     }
-    npend = 0;
 
     // ---- finished: publish the hit, free the lane ---------------------------------
     if (slot != VR_INVALID_ID && cur == VR_DONE) {
@@ -412,7 +416,7 @@ cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s) {
 // regeneration of finished slots
 // ---------------------------------------------------------------------------
 template <int D, int GEO>
-__global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ unsigned int shCount[12];
@@ -496,10 +500,8 @@ __global__ void __launch_bounds__(256) shadeKernel(const __grid_constant__ Trace
               id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (id[j] != VR_INVALID_ID) {
-                P[j] = __ldg(&sc.prim[2 * id[j]]);
-                Nn[j] = __ldg(&sc.prim[2 * id[j] + 1]);
-              }
+              if (id[j] != VR_INVALID_ID)
+                ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (id[j] != VR_INVALID_ID) {
