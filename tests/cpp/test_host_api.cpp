@@ -1,0 +1,360 @@
+// Parity tests of the C++ host mirror (include/viennaray_b200/*.hpp), written
+// the way the reference writes its own tests (tests/<name>/<name>.cpp of
+// ViennaRay v4.2.0): one block per reference test, same set-up, same asserts.
+//
+//   test_host_api cpu            blocks that need no device
+//   test_host_api gpu <outdir>   blocks that trace; flux arrays are dumped to
+//                                <outdir>/*.f32 for the Python side to compare
+//                                with the C-ABI / oracle path
+#include <rayParticle.hpp>
+#include <rayTraceDisk.hpp>
+#include <rayTraceTriangle.hpp>
+#include <rayTracingData.hpp>
+
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+using namespace viennaray;
+
+static int failures = 0;
+#define VC_TEST_ASSERT(cond)                                                                       \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      std::fprintf(stderr, "ASSERT FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);                \
+      ++failures;                                                                                  \
+    }                                                                                              \
+  } while (0)
+#define VC_TEST_ASSERT_ISCLOSE(a, b, eps) VC_TEST_ASSERT(std::fabs(double(a) - double(b)) <= (eps))
+
+// rayInternal::createPlaneGrid (rayUtil.hpp:324-351): same point order
+template <class T>
+static void planeGrid(T gridDelta, T extent, std::array<int, 3> dir, std::vector<Vec3D<T>> &points,
+                      std::vector<Vec3D<T>> &normals) {
+  Vec3D<T> point = {-extent, -extent, -extent}, normal = {0, 0, 0};
+  point[dir[2]] = 0;
+  normal[dir[2]] = 1;
+  points.clear();
+  normals.clear();
+  point[dir[0]] = -extent;
+  while (point[dir[0]] <= extent) {
+    point[dir[1]] = -extent;
+    while (point[dir[1]] <= extent) {
+      points.push_back(point);
+      normals.push_back(normal);
+      point[dir[1]] += gridDelta;
+    }
+    point[dir[0]] += gridDelta;
+  }
+}
+
+template <class T> static void dump(const std::string &path, const std::vector<T> &v) {
+  std::ofstream f(path, std::ios::binary);
+  f.write(reinterpret_cast<const char *>(v.data()), sizeof(T) * v.size());
+}
+
+// tests/tracingData/tracingData.cpp:11-35
+static void testTracingData() {
+  TracingData<float> defaultData;
+  defaultData.setNumberOfVectorData(2);
+  defaultData.setNumberOfScalarData(3);
+  defaultData.setScalarData(0, 1.f, "zero");
+  defaultData.setScalarData(1, 2.f, "one");
+  defaultData.setScalarData(2, 3.f);
+  defaultData.setVectorData(0, 1000, 0.f, "zero");
+  defaultData.setVectorData(1, 1000, 1.f, "one");
+  VC_TEST_ASSERT(defaultData.getVectorData(0).size() == 1000);
+  VC_TEST_ASSERT(defaultData.getVectorData("one")[999] == 1.f);
+  VC_TEST_ASSERT(defaultData.getScalarData("one") == 2.f);
+  VC_TEST_ASSERT(defaultData.getVectorDataLabel(1) == "one");
+  VC_TEST_ASSERT(defaultData.getScalarDataLabel(2) == "scalarData");
+  VC_TEST_ASSERT(defaultData.getVectorDataIndex("one") == 1);
+  TracingData<float> moved = std::move(defaultData);
+  VC_TEST_ASSERT(moved.getVectorData().size() == 2);
+  VC_TEST_ASSERT(moved.getScalarData().size() == 3);
+  moved.resizeAllVectorData(10, 2.f);
+  VC_TEST_ASSERT(moved.getVectorData(1).size() == 10 && moved.getVectorData(1)[3] == 2.f);
+  moved.appendVectorData(0, std::vector<float>{1.f, 2.f});
+  VC_TEST_ASSERT(moved.getVectorData(0).size() == 12);
+  moved.setVectorMergeType(0, TracingDataMergeEnum::APPEND);
+  VC_TEST_ASSERT(moved.getVectorMergeType(0) == TracingDataMergeEnum::APPEND);
+  VC_TEST_ASSERT(moved.getScalarMergeType(0) == TracingDataMergeEnum::SUM);
+}
+
+// tests/particle/particle.cpp:17-39
+static void testParticle() {
+  auto particle = std::make_unique<DiffuseParticle<float, 3>>(0.5f, "test");
+  VC_TEST_ASSERT(particle->getSourceDistributionPower() == 1.f);
+  VC_TEST_ASSERT(particle->getLocalDataLabels().size() == 1);
+  VC_TEST_ASSERT(particle->getLocalDataLabels()[0] == "test");
+  VC_TEST_ASSERT(particle->getMeanFreePath() == -1.f);
+  auto copy = particle->clone();
+  VC_TEST_ASSERT(copy->getLocalDataLabels()[0] == "test");
+  vr_particle_desc d{};
+  VC_TEST_ASSERT(copy->deviceParticle(d) && d.kind == VR_PARTICLE_DIFFUSE && d.sticking == 0.5f);
+  auto spec = std::make_unique<SpecularParticle<double, 2>>(1., 100., "s");
+  VC_TEST_ASSERT(spec->getSourceDistributionPower() == 100.);
+  VC_TEST_ASSERT(spec->deviceParticle(d) && d.kind == VR_PARTICLE_SPECULAR && d.sourcePower == 100.f);
+  auto ion = std::make_unique<ConedCosineParticle<float, 3>>(0.5f, 100.f, 1.4835f, "ion");
+  VC_TEST_ASSERT(ion->deviceParticle(d) && d.kind == VR_PARTICLE_CONED_COSINE);
+}
+
+// a user particle with host-side hooks: must be refused, never run on the CPU
+template <class T> class UserParticle : public Particle<UserParticle<T>, T> {
+public:
+  std::vector<std::string> getLocalDataLabels() const override { return {"user"}; }
+};
+
+// tests/smoothing/smoothing.cpp:43,50
+static void testSmoothing() {
+  std::vector<Vec3D<float>> points = {{0, 0, 0}, {1, 0, 0}, {2, 0, 0}, {0, 1, 0}, {1, 1, 0}, {2, 1, 0}};
+  std::vector<Vec3D<float>> normals = {{0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 1, 0}, {0, 1, 0}, {0, 1, 0}};
+  std::vector<float> flux = {1, 1, 1, 0, 0, 0};
+  TraceDisk<float, 3> trace;
+  trace.setGeometry(points, normals, 1.0f);
+  trace.smoothFlux(flux, 1);
+  for (int i = 0; i < 3; ++i)
+    VC_TEST_ASSERT_ISCLOSE(flux[i], 1.0, 1e-6);
+  for (int i = 3; i < 6; ++i)
+    VC_TEST_ASSERT_ISCLOSE(flux[i], 0.0, 1e-6);
+  std::vector<float> flux2 = {1, 1, 1, 0, 0, 0};
+  trace.smoothFlux(flux2, 2);
+  VC_TEST_ASSERT_ISCLOSE(flux2[0], 1.0, 1e-6);
+}
+
+// tests/pointNeighborhood/pointNeighborhood.cpp:51 and tests/diskAreas/diskAreas.cpp:76,79,96
+static void testNeighborsAndAreas() {
+  {
+    std::vector<Vec3D<float>> points, normals;
+    planeGrid<float>(0.5f, 10.f, {0, 1, 2}, points, normals);
+    TraceDisk<float, 3> trace;
+    trace.setGeometry(points, normals, 0.5f, 0.5f - 1e-6f);
+    auto bd = trace.getBoundingBox();
+    for (std::size_t i = 0; i < points.size(); ++i) {
+      const bool ex = points[i][0] == bd[0][0] || points[i][0] == bd[1][0];
+      const bool ey = points[i][1] == bd[0][1] || points[i][1] == bd[1][1];
+      const std::size_t expect = ex && ey ? 3 : (ex || ey ? 5 : 8);
+      VC_TEST_ASSERT(trace.getNeighborIndices(i).size() == expect);
+    }
+  }
+  {
+    std::vector<Vec3D<float>> points, normals;
+    planeGrid<float>(1.f, 2.f, {0, 1, 2}, points, normals);
+    TraceDisk<float, 3> trace;
+    trace.setGeometry(points, normals, 1.f);
+    const double r = 1.f * rayInternal::DiskFactor<3>;
+    const double whole = float(r) * float(r) * M_PI;
+    const auto bd = trace.getBoundingBox();
+    const auto &areas = trace.getDiskAreas(); // default boundary conditions: reflective
+    for (std::size_t i = 0; i < points.size(); ++i) {
+      const bool ex = points[i][0] == bd[0][0] || points[i][0] == bd[1][0];
+      const bool ey = points[i][1] == bd[0][1] || points[i][1] == bd[1][1];
+      const double expect = ex && ey ? whole / 4 : (ex || ey ? whole / 2 : whole);
+      VC_TEST_ASSERT_ISCLOSE(areas[i], expect, 1e-6);
+    }
+  }
+}
+
+// tests/buildBoundary/buildBoundary.cpp:34-39, tests/createGeometry/createGeometry.cpp:23-33
+static void testBoundingBox() {
+  std::array<std::array<float, 3>, 2> bb = {{{-1, -1, -1}, {1, 1, 1}}};
+  rayInternal::adjustBoundingBox<3>(bb, TraceDirection::POS_Z, 0.5f);
+  VC_TEST_ASSERT(bb[1][2] == 2.f && bb[0][2] == -1.f && bb[0][0] == -1.f && bb[1][1] == 1.f);
+  bb = {{{-1, -1, 0}, {1, 1, 0}}};
+  rayInternal::adjustBoundingBox<2>(bb, TraceDirection::NEG_Y, 0.25f);
+  VC_TEST_ASSERT(bb[0][1] == -1.5f && bb[0][2] == -0.25f && bb[1][2] == 0.25f);
+  const auto st = rayInternal::getTraceSettings(TraceDirection::POS_Y);
+  VC_TEST_ASSERT(st[0] == 1 && st[1] == 0 && st[2] == 2 && st[3] == 1 && st[4] == -1);
+  const auto b = rayInternal::getOrthonormalBasis({1.f, 1.f, -1.f});
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double d = 0;
+      for (int k = 0; k < 3; ++k)
+        d += double(b[i][k]) * b[j][k];
+      VC_TEST_ASSERT_ISCLOSE(d, i == j ? 1. : 0., 1e-6);
+    }
+}
+
+// no device: apply() must fail loudly (error flag), not fall back to host code
+static void testNoFallback() {
+  std::vector<Vec3D<float>> points, normals;
+  planeGrid<float>(0.5f, 1.f, {0, 1, 2}, points, normals);
+  TraceDisk<float, 3> trace;
+  trace.setGeometry(points, normals, 0.5f);
+  auto particle = std::make_unique<DiffuseParticle<float, 3>>(1.f, "flux");
+  trace.setParticleType(particle);
+  trace.setNumberOfRaysPerPoint(10);
+  trace.apply();
+  if (trace.getDeviceContext() == nullptr)
+    VC_TEST_ASSERT(trace.getRayTraceInfo().error);
+  TraceDisk<float, 3> noParticle;
+  noParticle.setGeometry(points, normals, 0.5f);
+  noParticle.apply();
+  VC_TEST_ASSERT(noParticle.getRayTraceInfo().error);
+}
+
+// ------------------------------------------------------------------ device blocks
+// tests/rngSeed/rngSeed.cpp:29,41,48-51
+static void testRngSeed(const std::string &out) {
+  std::vector<Vec3D<float>> points, normals;
+  planeGrid<float>(0.5f, 5.f, {0, 1, 2}, points, normals);
+  std::vector<float> flux[2];
+  for (int run = 0; run < 2; ++run) {
+    TraceDisk<float, 3> tracer;
+    auto particle = std::make_unique<DiffuseParticle<float, 3>>(1.0f, "flux");
+    tracer.setGeometry(points, normals, 0.5f);
+    tracer.setNumberOfRaysPerPoint(10);
+    tracer.setParticleType(particle);
+    tracer.setRngSeed(12345);
+    tracer.apply();
+    VC_TEST_ASSERT(!tracer.getRayTraceInfo().error);
+    flux[run] = tracer.getLocalData().getVectorData("flux");
+  }
+  VC_TEST_ASSERT(flux[0].size() == 441);
+  VC_TEST_ASSERT(std::memcmp(flux[0].data(), flux[1].data(), sizeof(float) * 441) == 0);
+  dump(out + "/rngSeed_flux.f32", flux[0]);
+}
+
+// tests/traceInterface/traceInterface.cpp:55-67
+static void testTraceInterface(const std::string &out) {
+  std::vector<Vec3D<float>> points, normals;
+  planeGrid<float>(0.5f, 5.f, {0, 1, 2}, points, normals);
+  std::vector<int> matIds(points.size(), 0);
+  BoundaryCondition bc[3] = {BoundaryCondition::REFLECTIVE_BOUNDARY, BoundaryCondition::REFLECTIVE_BOUNDARY,
+                             BoundaryCondition::REFLECTIVE_BOUNDARY};
+  auto particle = std::make_unique<DiffuseParticle<float, 3>>(0.5f, "hitFlux");
+  TracingData<float> globalData;
+  globalData.setNumberOfVectorData(1);
+
+  TraceDisk<float, 3> rayTracer;
+  rayTracer.setParticleType(particle);
+  rayTracer.setGeometry(points, normals, 0.5f);
+  rayTracer.setBoundaryConditions(bc);
+  rayTracer.setMaterialIds(matIds);
+  rayTracer.setGlobalData(globalData);
+  rayTracer.setSourceDirection(TraceDirection::POS_Z);
+  rayTracer.setNumberOfRaysPerPoint(10);
+  rayTracer.setUseRandomSeeds(false);
+  rayTracer.setMaxBoundaryHits(10);
+  rayTracer.apply();
+  auto info = rayTracer.getRayTraceInfo();
+  VC_TEST_ASSERT(!info.error);
+  VC_TEST_ASSERT(info.numRays == 4410);
+  VC_TEST_ASSERT(info.totalRaysTraced >= info.numRays);
+  VC_TEST_ASSERT(info.geometryHits > 0 && info.nonGeometryHits > 0);
+  auto flux = rayTracer.getLocalData().getVectorData("hitFlux");
+  dump(out + "/traceInterface_raw.f32", flux);
+  rayTracer.normalizeFlux(flux);
+  rayTracer.smoothFlux(flux, 2);
+  double mean = 0;
+  for (auto f : flux)
+    mean += f;
+  mean /= flux.size();
+  VC_TEST_ASSERT(mean > 0.5 && mean < 1.5); // open plane under a cosine source: flux ~ 1
+  dump(out + "/traceInterface_norm.f32", flux);
+
+  // run number advances: a second apply() draws a different stream
+  rayTracer.apply();
+  auto flux2 = rayTracer.getLocalData().getVectorData("hitFlux");
+  VC_TEST_ASSERT(std::memcmp(flux2.data(), rayTracer.getLocalData().getVectorData(0).data(), 4 * 441) == 0);
+  dump(out + "/traceInterface_run2.f32", flux2);
+
+  // host-side hooks cannot run on the device: explicit error, no fallback
+  TraceDisk<float, 3> userTracer;
+  auto user = std::make_unique<UserParticle<float>>();
+  userTracer.setParticleType(user);
+  userTracer.setGeometry(points, normals, 0.5f);
+  userTracer.apply();
+  VC_TEST_ASSERT(userTracer.getRayTraceInfo().error);
+}
+
+// examples/triangle3D-style run on a two-triangle floor + tests/trace2D
+static void testTriangleAnd2D(const std::string &out) {
+  {
+    std::vector<Vec3D<float>> nodes = {{-5, -5, 0}, {5, -5, 0}, {5, 5, 0}, {-5, 5, 0}};
+    std::vector<Vec3D<unsigned>> tris = {{0, 1, 2}, {0, 2, 3}};
+    TraceTriangle<float, 3> tracer;
+    auto particle = std::make_unique<DiffuseParticle<float, 3>>(1.0f, "flux");
+    tracer.setGeometry(nodes, tris, 1.0f);
+    tracer.setParticleType(particle);
+    tracer.setNumberOfRaysFixed(20000);
+    tracer.setRngSeed(7);
+    tracer.apply();
+    auto info = tracer.getRayTraceInfo();
+    VC_TEST_ASSERT(!info.error && info.numRays == 20000);
+    auto flux = tracer.getLocalData().getVectorData(0);
+    VC_TEST_ASSERT_ISCLOSE(flux[0] + flux[1], 20000., 0.5); // every ray lands on the floor once
+    tracer.normalizeFlux(flux);
+    VC_TEST_ASSERT_ISCLOSE(flux[0], 1.0, 0.05);
+    VC_TEST_ASSERT_ISCLOSE(flux[1], 1.0, 0.05);
+    dump(out + "/triangle_norm.f32", flux);
+  }
+  {
+    std::vector<Vec2D<float>> points, normals;
+    for (float x = -10.f; x <= 10.f; x += 0.5f) {
+      points.push_back({x, 0.f});
+      normals.push_back({0.f, 1.f});
+    }
+    BoundaryCondition bc[2] = {BoundaryCondition::PERIODIC_BOUNDARY, BoundaryCondition::PERIODIC_BOUNDARY};
+    TraceDisk<float, 2> tracer;
+    auto particle = std::make_unique<DiffuseParticle<float, 2>>(0.1f, "flux");
+    tracer.setGeometry(points, normals, 0.5f);
+    tracer.setBoundaryConditions(bc);
+    tracer.setParticleType(particle);
+    tracer.setNumberOfRaysPerPoint(2000);
+    tracer.setRngSeed(3);
+    tracer.apply();
+    VC_TEST_ASSERT(!tracer.getRayTraceInfo().error);
+    auto flux = tracer.getLocalData().getVectorData(0);
+    tracer.normalizeFlux(flux);
+    tracer.smoothFlux(flux);
+    for (std::size_t i = 2; i + 2 < flux.size(); ++i)
+      VC_TEST_ASSERT_ISCLOSE(flux[i], 1.0, 0.08);
+    dump(out + "/disk2D_norm.f32", flux);
+  }
+}
+
+// areas <in.bin> <out.f64>: disk areas of a point cloud under periodic boundaries
+// (input: uint32 n, float gridDelta, n x 3 points, n x 3 normals), for the
+// comparison with the reference's GeometryDisk::computeDiskAreas
+static int areasTool(const char *in, const char *out) {
+  std::ifstream f(in, std::ios::binary);
+  std::uint32_t n = 0;
+  float gd = 0;
+  f.read(reinterpret_cast<char *>(&n), 4);
+  f.read(reinterpret_cast<char *>(&gd), 4);
+  std::vector<Vec3D<float>> pts(n), nrm(n);
+  f.read(reinterpret_cast<char *>(pts.data()), 12 * n);
+  f.read(reinterpret_cast<char *>(nrm.data()), 12 * n);
+  BoundaryCondition bc[3] = {BoundaryCondition::PERIODIC_BOUNDARY, BoundaryCondition::PERIODIC_BOUNDARY,
+                             BoundaryCondition::PERIODIC_BOUNDARY};
+  TraceDisk<float, 3> trace;
+  trace.setGeometry(pts, nrm, gd);
+  trace.setBoundaryConditions(bc);
+  dump(out, trace.getDiskAreas());
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  const std::string mode = argc > 1 ? argv[1] : "cpu";
+  if (mode == "areas" && argc > 3)
+    return areasTool(argv[2], argv[3]);
+  testTracingData();
+  testParticle();
+  testSmoothing();
+  testNeighborsAndAreas();
+  testBoundingBox();
+  testNoFallback();
+  if (mode == "gpu") {
+    const std::string out = argc > 2 ? argv[2] : ".";
+    testRngSeed(out);
+    testTraceInterface(out);
+    testTriangleAnd2D(out);
+  }
+  if (failures) {
+    std::fprintf(stderr, "%d assertion(s) failed\n", failures);
+    return 1;
+  }
+  std::printf("test_host_api %s: ok\n", mode.c_str());
+  return 0;
+}
