@@ -171,8 +171,9 @@ int vr_debug_reflect(vr_ctx *ctx, int kind, int D, const float *rayDir, const fl
 int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out5);
 /* per-ray traversal work counters of the last vr_trace* call when the
  * context was created with VR_COUNT_WORK=1 in the environment: out[0] node
- * visits, out[1] primitive tests, out[2] neighbour tests, out[3] flux adds */
-int vr_debug_work_counters(vr_ctx *ctx, uint64_t *out4);
+ * visits, out[1] primitive tests, out[2] neighbour tests, out[3] flux adds,
+ * out[4] rays finished by the sky map without a traversal */
+int vr_debug_work_counters(vr_ctx *ctx, uint64_t *out5);
 
 #ifdef __cplusplus
 }

@@ -24,5 +24,5 @@ for name, p in (("neutral", capi.ParticleDesc(0, 0.1, 1.0, 0.0)),
     print(name, {k: round(v / rays, 3) for k, v in w.items()},
           "traces/ray %.3f geo %.3f miss %.3f" % (i.totalRaysTraced / rays, i.geometryHits / rays,
                                                  i.nonGeometryHits / rays),
-          "nodes/trace %.2f prims/trace %.2f" % (w["node_visits"] / i.totalRaysTraced,
+          "sky_finished/ray %.3f" % (w["sky_finished"] / rays), "nodes/trace %.2f prims/trace %.2f" % (w["node_visits"] / i.totalRaysTraced,
                                                 w["prim_tests"] / i.totalRaysTraced))

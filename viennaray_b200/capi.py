@@ -287,7 +287,7 @@ class Context:
                 "node_bytes": int(out[3]), "build_ms": float(build_ms)}
 
     def work_counters(self):
-        out = np.zeros(4, np.uint64)
+        out = np.zeros(5, np.uint64)
         self._ck(self.L.vr_debug_work_counters(self.h, _p(out)))
         return {"node_visits": int(out[0]), "prim_tests": int(out[1]), "nb_tests": int(out[2]),
-                "flux_adds": int(out[3])}
+                "flux_adds": int(out[3]), "sky_finished": int(out[4])}

@@ -58,6 +58,11 @@ struct vr_ctx {
   int kernelLaunches = 0;
   int iterations = 0;
   bool countWork = false;
+  // sky map (escape culling), built lazily for the source axis / side of a trace
+  float2 *dSky = nullptr;
+  int skyAxis = -1;
+  float skySign = 0.f, skyTop = 0.f;
+  int skyCells = 128;  // VR_SKY_CELLS; 0 disables the map
   bool timeKernels = false;  // VR_TIME_KERNELS=1: CUDA events around every launch
   std::vector<cudaEvent_t> tev;
   std::vector<int> tevKind;
@@ -91,6 +96,9 @@ static void freeDeviceScene(vr_ctx *c) {
   c->dPrim = nullptr;
   c->dNbOff = c->dNbIdx = nullptr;
   freeBvh(&c->bvh, c->stream);
+  cudaFreeAsync(c->dSky, c->stream);
+  c->dSky = nullptr;
+  c->skyAxis = -1;
   c->committed = false;
 }
 static void freeInputs(vr_ctx *c) {
@@ -239,6 +247,11 @@ int vr_ctx_create(int cudaDevice, vr_ctx **out) {
   ctx->numSMs = prop.multiProcessorCount;
   const char *cw = getenv("VR_COUNT_WORK");
   ctx->countWork = cw && cw[0] == '1';
+  if (const char *sk = getenv("VR_SKY_CELLS")) {
+    long v = atol(sk);
+    if (v >= 0 && v <= 1024)
+      ctx->skyCells = (int)v;
+  }
   const char *tk = getenv("VR_TIME_KERNELS");
   ctx->timeKernels = tk && tk[0] == '1';
   if (const char *ps = getenv("VR_POOL_SLOTS")) {
@@ -258,7 +271,7 @@ int vr_ctx_create(int cudaDevice, vr_ctx **out) {
       (e = cudaEventCreateWithFlags(&ctx->liveEv[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->liveEv[2], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->liveEv[3], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->dWork, 4 * sizeof(unsigned long long))) != cudaSuccess) {
+      (e = cudaMalloc(&ctx->dWork, 8 * sizeof(unsigned long long))) != cudaSuccess) {
     failCuda(nullptr, e, "vr_ctx_create");
     vr_ctx_destroy(ctx);
     return VR_ERR_CUDA;
@@ -527,6 +540,7 @@ int vr_scene_commit(vr_ctx *ctx) {
   s.nbIdx = ctx->dNbIdx;
   s.nodes = ctx->bvh.nodes;
   s.rootRef = ctx->bvh.rootRef;
+  s.sky = nullptr;  // rebuilt by the next trace
   ctx->committed = true;
   return VR_OK;
 }
@@ -588,12 +602,42 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
   ctx->lastNumRays = cfg ? cfg->rayIdxEnd - cfg->rayIdxBegin : 0;
   CK(cudaMemsetAsync(ctx->dResult, 0, sizeof(unsigned long long) * words, ctx->stream));
   if (ctx->countWork)
-    CK(cudaMemsetAsync(ctx->dWork, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->dWork, 0, 8 * sizeof(unsigned long long), ctx->stream));
   ctx->kernelLaunches = 0;
   ctx->iterations = 0;
   const uint64_t shardRays = cfg ? cfg->rayIdxEnd - cfg->rayIdxBegin : 0;
   const uint32_t slots = (uint32_t)std::min<uint64_t>(ctx->poolSlots, std::max<uint64_t>(shardRays, 1));
   CK(ensurePool(ctx, slots));
+  // sky map of this source side (3D only): rays that provably meet no primitive
+  // are finished inside the shade kernel instead of being traversed
+  if (ctx->D == 3 && ctx->skyCells > 0 && src && src->rayDir >= 0 && src->rayDir <= 2) {
+    const float sign = src->posNeg < 0.f ? 1.f : -1.f;  // towards the source plane
+    if (ctx->skyAxis != src->rayDir || ctx->skySign != sign || !ctx->dSky) {
+      const int G = ctx->skyCells;
+      if (!ctx->dSky)
+        CK(cudaMallocAsync(&ctx->dSky, sizeof(float2) * G * G, ctx->stream));
+      DeviceScene &s = ctx->scene;
+      s.skyA = ctx->scene.firstDir;
+      s.skyB = ctx->scene.secondDir;
+      const float lo[2] = {ctx->geoLo[s.skyA], ctx->geoLo[s.skyB]};
+      const float hi[2] = {ctx->geoHi[s.skyA], ctx->geoHi[s.skyB]};
+      CK(buildSky(s, G, src->rayDir, sign, s.skyA, s.skyB, lo, hi, ctx->dSky, &ctx->skyTop,
+                  ctx->stream));
+      ctx->skyAxis = src->rayDir;
+      ctx->skySign = sign;
+      s.sky = ctx->dSky;
+      s.skyN = G;
+      s.skyUp = src->rayDir;
+      s.skySign = sign;
+      for (int k = 0; k < 2; ++k) {
+        s.skyLo[k] = lo[k];
+        s.skyInv[k] = hi[k] > lo[k] ? (float)G / (hi[k] - lo[k]) : 0.f;
+      }
+      s.skyTop = ctx->skyTop;
+    }
+  } else {
+    ctx->scene.sky = nullptr;
+  }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int k = 0; k < np; ++k) {
     TraceParams p;
@@ -1009,14 +1053,14 @@ int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out5) {
   return VR_OK;
 }
 
-int vr_debug_work_counters(vr_ctx *ctx, uint64_t *out4) {
-  if (!ctx || !out4)
+int vr_debug_work_counters(vr_ctx *ctx, uint64_t *out5) {
+  if (!ctx || !out5)
     return VR_ERR_ARGUMENT;
   if (!ctx->countWork)
     return fail(ctx, VR_ERR_STATE, "vr_debug_work_counters: set VR_COUNT_WORK=1 before create");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemcpy(out4, ctx->dWork, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out5, ctx->dWork, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return VR_OK;
 }
 

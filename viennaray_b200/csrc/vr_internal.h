@@ -38,6 +38,15 @@ struct DeviceScene {
   const Node2 *nodes;
   uint32_t rootRef;
   float qLo[3], qScale[3];  // node box coordinate = qLo + q * qScale
+  // sky map (vr_scene.cu buildSky): a G x G grid over the two lateral axes; per
+  // cell {base, slope}.  A ray that leaves a surface point of the cell towards
+  // the source with a steeper slope than `slope` cannot touch any primitive
+  // (slope = +inf: no statement for this cell).  sky == nullptr: disabled.
+  const float2 *sky;
+  int skyN, skyUp, skyA, skyB;  // grid size, source axis, lateral axes
+  float skySign;                // height = skySign * coordinate[skyUp]
+  float skyLo[2], skyInv[2];    // cell = (lateral - skyLo) * skyInv
+  float skyTop;                 // height of the highest primitive point
   // boundary (rayBoundary.hpp:164-245)
   float bbox[2][3];
   int firstDir, secondDir;
@@ -105,6 +114,12 @@ cudaError_t launchGatherPrims(int geoType, const float4 *A, const float4 *B, con
 cudaError_t remapNeighbors(const uint32_t *s2o, const uint32_t *offO, const uint32_t *idxO,
                            uint32_t n, uint32_t *o2s, uint32_t *cnt, uint32_t *off, uint32_t *idx,
                            cudaStream_t s);
+
+// sky map for rays that travel towards the source (see DeviceScene::sky).
+// table: G*G float2, device.  top: host out.
+cudaError_t buildSky(const DeviceScene &sc, int G, int upAxis, float upSign, int axisA, int axisB,
+                     const float lo[2], const float hi[2], float2 *table, float *topOut,
+                     cudaStream_t s);
 
 // ---- kernels (vr_trace.cu) -------------------------------------------------
 cudaError_t launchDiskBounds(const float4 *xyzr, const float4 *nrm, uint32_t n, float4 *lo,

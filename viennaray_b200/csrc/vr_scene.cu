@@ -6,6 +6,8 @@
 // Embree (rayGeometryDisk.hpp:102-193, rayGeometryTriangle.hpp:15-92).
 #include <cub/device/device_scan.cuh>
 
+#include <cstring>
+
 #include "vr_internal.h"
 
 namespace vr {
@@ -84,7 +86,176 @@ __global__ void closeOffsetsKernel(const uint32_t *cnt, uint32_t n, uint32_t *of
   off[n] = off[n - 1] + cnt[n - 1];
 }
 
+// ---- sky map ------------------------------------------------------------------------
+// order-preserving map float -> uint for atomicMin / atomicMax
+__device__ __forceinline__ unsigned int f2o(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float o2f(unsigned int o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ float axisOf(const float4 &v, int a) {
+  return a == 0 ? v.x : (a == 1 ? v.y : v.z);
+}
+
+__global__ void skyInitKernel(unsigned int *hMax, unsigned int *hMin, int cells) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cells) {
+    hMax[i] = 0u;           // below every float
+    hMin[i] = 0xffffffffu;  // above every float
+  }
+}
+
+// every primitive stamps the height range of its surface into the cells its
+// (padded) lateral extent overlaps.  Heights of primitives that are exactly
+// perpendicular to the source axis are not padded, so that coplanar flat
+// neighbourhoods compare equal.
+__global__ void skyStampKernel(DeviceScene sc, int G, int up, float sign, int aA, int aB, float loA,
+                               float loB, float invA, float invB, unsigned int *hMax,
+                               unsigned int *hMin, unsigned int *topOut) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  float cLo[2] = {0.f, 0.f}, cHi[2] = {0.f, 0.f}, hLo = 0.f, hHi = __uint_as_float(0xff800000u);
+  const bool valid = i < sc.numPrims;
+  if (!valid) {
+  } else if (sc.geoType == 0) {
+    const float4 P = sc.prim[2 * i], N = sc.prim[2 * i + 1];
+    const float nn = (N.x * N.x + N.y * N.y) + N.z * N.z;
+    const int ax[3] = {aA, aB, up};
+    float ext[3];
+    for (int k = 0; k < 3; ++k) {
+      const float na = axisOf(N, ax[k]);
+      const float f = nn > 0.f ? 1.f - na * na / nn : 1.f;
+      ext[k] = P.w * sqrtf(fmaxf(f, 0.f));
+    }
+    for (int k = 0; k < 2; ++k) {
+      const float c = axisOf(P, ax[k]);
+      const float pad = 1e-3f * P.w + 1e-5f * fabsf(c);
+      cLo[k] = c - ext[k] - pad;
+      cHi[k] = c + ext[k] + pad;
+    }
+    const float ch = sign * axisOf(P, up);
+    const float padH = ext[2] > 0.f ? 1e-5f * (P.w + fabsf(ch)) : 0.f;
+    hLo = ch - ext[2] - padH;
+    hHi = ch + ext[2] + padH;
+  } else {
+    const float4 a = sc.prim[4 * i], b = sc.prim[4 * i + 1], c = sc.prim[4 * i + 2];
+    const int ax[2] = {aA, aB};
+    for (int k = 0; k < 2; ++k) {
+      const float x0 = axisOf(a, ax[k]), x1 = axisOf(b, ax[k]), x2 = axisOf(c, ax[k]);
+      const float l = fminf(x0, fminf(x1, x2)), h = fmaxf(x0, fmaxf(x1, x2));
+      const float pad = 1e-4f * (h - l) + 1e-5f * fmaxf(fabsf(l), fabsf(h)) + 1e-6f;
+      cLo[k] = l - pad;
+      cHi[k] = h + pad;
+    }
+    const float z0 = sign * axisOf(a, up), z1 = sign * axisOf(b, up), z2 = sign * axisOf(c, up);
+    hLo = fminf(z0, fminf(z1, z2));
+    hHi = fmaxf(z0, fmaxf(z1, z2));
+  }
+  {  // highest point of the scene: warp maximum, one atomic per warp
+    float t = hHi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if ((threadIdx.x & 31) == 0)
+      atomicMax(topOut, f2o(t));
+  }
+  if (!valid)
+    return;
+  const int i0 = max(0, min(G - 1, (int)floorf((cLo[0] - loA) * invA)));
+  const int i1 = max(0, min(G - 1, (int)floorf((cHi[0] - loA) * invA)));
+  const int j0 = max(0, min(G - 1, (int)floorf((cLo[1] - loB) * invB)));
+  const int j1 = max(0, min(G - 1, (int)floorf((cHi[1] - loB) * invB)));
+  for (int ia = i0; ia <= i1; ++ia)
+    for (int jb = j0; jb <= j1; ++jb) {
+      atomicMax(&hMax[ia * G + jb], f2o(hHi));
+      atomicMin(&hMin[ia * G + jb], f2o(hLo));
+    }
+}
+
+// one block per cell: flat 3 x 3 neighbourhood?  then the steepest sight line
+// from the cell's base height to the top of any farther cell
+__global__ void skySlopeKernel(const unsigned int *hMax, const unsigned int *hMin, int G, float wA,
+                               float wB, float2 *table) {
+  const int c = blockIdx.x, ca = c / G, cb = c % G;
+  __shared__ float red[256];
+  const unsigned int oMin = hMin[c];
+  const float inf = __uint_as_float(0x7f800000u);
+  if (oMin == 0xffffffffu) {  // no primitive touches the cell
+    if (threadIdx.x == 0)
+      table[c] = make_float2(inf, inf);
+    return;
+  }
+  const float base = o2f(oMin);
+  bool flat = true;
+  for (int da = -1; da <= 1; ++da)
+    for (int db = -1; db <= 1; ++db) {
+      const int na = ca + da, nb = cb + db;
+      if (na < 0 || nb < 0 || na >= G || nb >= G)
+        continue;
+      const unsigned int o = hMax[na * G + nb];
+      if (o != 0u && o2f(o) > base)
+        flat = false;
+    }
+  float slope = 0.f;
+  for (int k = threadIdx.x; k < G * G; k += blockDim.x) {
+    const unsigned int o = hMax[k];
+    if (o == 0u)
+      continue;
+    const float h = o2f(o);
+    const int ka = k / G, kb = k % G;
+    const int ga = abs(ka - ca) - 1, gb = abs(kb - cb) - 1;
+    if (ga <= 0 && gb <= 0)
+      continue;  // the 3 x 3 neighbourhood: covered by the flatness test
+    const float dx = fmaxf((float)ga, 0.f) * wA, dy = fmaxf((float)gb, 0.f) * wB;
+    const float gap = sqrtf(dx * dx + dy * dy) * 0.999f;
+    slope = fmaxf(slope, (h - base) / gap);
+  }
+  red[threadIdx.x] = slope;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+      red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    table[c] = make_float2(base, flat ? red[0] : inf);
+}
+
+__global__ void skyTopKernel(unsigned int *top) { *top = __float_as_uint(o2f(*top)); }
+
 }  // namespace
+
+cudaError_t buildSky(const DeviceScene &sc, int G, int upAxis, float upSign, int axisA, int axisB,
+                     const float lo[2], const float hi[2], float2 *table, float *topOut,
+                     cudaStream_t s) {
+  unsigned int *hMax = nullptr, *hMin = nullptr, *top = nullptr;
+  const int cells = G * G;
+  cudaError_t e = cudaMallocAsync(&hMax, sizeof(unsigned int) * (2 * cells + 1), s);
+  if (e != cudaSuccess)
+    return e;
+  hMin = hMax + cells;
+  top = hMin + cells;
+  const float wA = (hi[0] - lo[0]) / (float)G, wB = (hi[1] - lo[1]) / (float)G;
+  const float invA = wA > 0.f ? 1.f / wA : 0.f, invB = wB > 0.f ? 1.f / wB : 0.f;
+  skyInitKernel<<<(cells + 255) / 256, 256, 0, s>>>(hMax, hMin, cells);
+  cudaMemsetAsync(top, 0, sizeof(unsigned int), s);
+  skyStampKernel<<<(sc.numPrims + 255) / 256, 256, 0, s>>>(
+      sc, G, upAxis, upSign, axisA, axisB, lo[0], lo[1], invA, invB, hMax, hMin, top);
+  skySlopeKernel<<<cells, 256, 0, s>>>(hMax, hMin, G, wA, wB, table);
+  skyTopKernel<<<1, 1, 0, s>>>(top);
+  e = cudaGetLastError();
+  unsigned int bits = 0;
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(&bits, top, sizeof(bits), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(s);
+  cudaFreeAsync(hMax, s);
+  float t;
+  memcpy(&t, &bits, 4);
+  *topOut = t;
+  return e;
+}
 
 cudaError_t launchPackDiskNormals(const float *nxyz, uint32_t n, float4 *B, cudaStream_t s) {
   packDiskNormalsKernel<<<(n + 255) / 256, 256, 0, s>>>(nxyz, n, B);

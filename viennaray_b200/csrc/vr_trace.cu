@@ -84,6 +84,32 @@ __device__ __forceinline__ void storeBoundaryHit(const DeviceScene &sc, const Ra
   pool.hit[s] = make_float4(best.t, __uint_as_float(best.prim), __uint_as_float(best.geom), 0.f);
 }
 
+// Sky test: may the ray leaving `org` towards the source be declared free of
+// any primitive?  Yes when (a) its cell of the sky map is flat with its
+// neighbourhood and the ray is steeper than every sight line from the cell's
+// base height to the tops of all farther cells, (b) it starts at or above that
+// base, and (c) it rises above the highest primitive before it reaches a
+// lateral boundary (tBoundary), so that no periodic / mirrored image matters.
+__device__ __forceinline__ bool skyEscapes(const DeviceScene &sc, const V3 &org, const V3 &dir,
+                                           float tBoundary) {
+  const float up = sc.skySign * comp(dir, sc.skyUp);
+  if (!(up > 0.05f))
+    return false;
+  const float la = comp(dir, sc.skyA), lb = comp(dir, sc.skyB);
+  const float lat = sqrtf(la * la + lb * lb);
+  const int G = sc.skyN;
+  const int ca = min(G - 1, max(0, (int)floorf((comp(org, sc.skyA) - sc.skyLo[0]) * sc.skyInv[0])));
+  const int cb = min(G - 1, max(0, (int)floorf((comp(org, sc.skyB) - sc.skyLo[1]) * sc.skyInv[1])));
+  const float2 cell = __ldg(&sc.sky[ca * G + cb]);  // {base, slope}
+  const float h0 = sc.skySign * comp(org, sc.skyUp);
+  if (!(up > (cell.y * 1.001f + 1e-4f) * lat))
+    return false;
+  if (!(h0 + VR_TNEAR * up > cell.x + 1e-6f * fmaxf(1.f, fabsf(cell.x))))
+    return false;
+  const float tTop = (sc.skyTop - h0) / up;
+  return tTop * 1.0001f + 1e-5f < tBoundary;
+}
+
 __device__ __forceinline__ unsigned long long warpSum(unsigned long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -426,6 +452,7 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
   const uint32_t numSlots = *p.slotCount;
 
   unsigned cTraces = 0, cMiss = 0, cGeo = 0, cBnd = 0, cRefl = 0, cTerm = 0, wNb = 0, wFlux = 0;
+  unsigned wSky = 0;
   bool live = false, finish = false;
   float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
   if (s < numSlots)
@@ -436,7 +463,10 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
   float w = 0.f;
   uint64_t idx = 0;
   uint32_t numReflections = 0, boundaryHits = 0;
-  bool hitFromBack = false, rngLoaded = false;
+  bool hitFromBack = false, rngLoaded = false, bhValid = false;
+  Hit bh;
+  bh.t = 0.f;
+  bh.geom = bh.prim = bh.orig = VR_INVALID_ID;
   Rng rng;
   rng.init(0, 0, 0);
 
@@ -537,6 +567,38 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
             dir = fillDir<D>(rayDirection);
           }
         }
+        if (D == 3 && !finish && sc.sky != nullptr) {
+          // boundary hit of the reflected ray (needed anyway); if the sky map proves
+          // that the ray meets no primitive, walk it through the boundary to its
+          // end right here: it never needs a traversal
+          bh.t = 3.402823466e+38f;
+          bh.geom = bh.prim = bh.orig = VR_INVALID_ID;
+          boundaryTest(sc, org, dir, bh);
+          bhValid = true;
+          if (skyEscapes(sc, org, dir, bh.t)) {
+            ++wSky;
+            for (;;) {
+              ++cTraces;
+              if (bh.geom == VR_INVALID_ID) {
+                ++cMiss;
+                finish = true;
+                break;
+              }
+              if (++boundaryHits > p.maxBoundaryHits) {
+                ++cTerm;
+                finish = true;
+                break;
+              }
+              if (!boundaryHit<D>(sc, org, rayDirection, dir, bh.prim, bh.t)) {
+                finish = true;
+                break;
+              }
+              bh.t = 3.402823466e+38f;
+              bh.geom = bh.prim = bh.orig = VR_INVALID_ID;
+              boundaryTest(sc, org, dir, bh);
+            }
+          }
+        }
         if (!finish)
           p.pool.rng[s] = rng.save();
       }
@@ -566,8 +628,12 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
       } else {
         p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
       }
-      if (survive)
-        storeBoundaryHit(sc, p.pool, s, org, dir);
+      if (survive) {
+        if (!finish && bhValid)  // the boundary hit of this ray is known already
+          p.pool.hit[s] = make_float4(bh.t, __uint_as_float(bh.prim), __uint_as_float(bh.geom), 0.f);
+        else
+          storeBoundaryHit(sc, p.pool, s, org, dir);
+      }
     }
   } else {
     const unsigned m = __ballot_sync(0xffffffffu, survive);
@@ -588,60 +654,42 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
         } else {
           storeRay<D>(p.poolOut, dst, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
         }
-        storeBoundaryHit(sc, p.poolOut, dst, org, dir);
+        if (!finish && bhValid)
+          p.poolOut.hit[dst] =
+              make_float4(bh.t, __uint_as_float(bh.prim), __uint_as_float(bh.geom), 0.f);
+        else
+          storeBoundaryHit(sc, p.poolOut, dst, org, dir);
       }
     }
   }
   const bool stillLive = survive && !p.compact;  // compact mode counted them above
 
-  // ---- counters: warp -> block -> one global atomic per block and counter ----------
+  // ---- counters: warp (REDUX) -> block -> one global atomic per block and counter ----
   const unsigned lane = threadIdx.x & 31u;
-  unsigned vals[9] = {cTraces, cMiss, cGeo, cBnd, cRefl, cTerm, stillLive ? 1u : 0u, wNb, wFlux};
+  const unsigned vals[10] = {cTraces, cMiss, cGeo,  cBnd,  cRefl,
+                             cTerm,   stillLive ? 1u : 0u, wNb, wFlux, wSky};
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    unsigned v = vals[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      v += __shfl_down_sync(0xffffffffu, v, o);
+  for (int k = 0; k < 10; ++k) {
+    if (k >= 7 && !p.work)
+      continue;
+    const unsigned v = __reduce_add_sync(0xffffffffu, vals[k]);
     if (lane == 0 && v)
       atomicAdd(&shCount[k], v);
   }
   __syncthreads();
-  if (threadIdx.x < 9) {
+  if (threadIdx.x < 10) {
     const unsigned v = shCount[threadIdx.x];
     if (v) {
       unsigned long long *cnt = p.counters + (size_t)(blockIdx.x % VR_COUNTER_COPIES) * 8;
-      switch (threadIdx.x) {
-      case 0:
-        atomicAdd(&cnt[1], (unsigned long long)v);
-        break;
-      case 1:
-        atomicAdd(&cnt[2], (unsigned long long)v);
-        break;
-      case 2:
-        atomicAdd(&cnt[3], (unsigned long long)v);
-        break;
-      case 3:
-        atomicAdd(&cnt[5], (unsigned long long)v);
-        break;
-      case 4:
-        atomicAdd(&cnt[6], (unsigned long long)v);
-        break;
-      case 5:
-        atomicAdd(&cnt[7], (unsigned long long)v);
-        break;
-      case 6:
+      // TraceInfo slots: 1 traces, 2 misses, 3 geometry hits, 5 boundary hits,
+      // 6 reflections, 7 terminated
+      const int slotOf[6] = {1, 2, 3, 5, 6, 7};
+      if (threadIdx.x < 6)
+        atomicAdd(&cnt[slotOf[threadIdx.x]], (unsigned long long)v);
+      else if (threadIdx.x == 6)
         atomicAdd(p.liveCount, v);
-        break;
-      case 7:
-        if (p.work)
-          atomicAdd(&p.work[2], (unsigned long long)v);
-        break;
-      default:
-        if (p.work)
-          atomicAdd(&p.work[3], (unsigned long long)v);
-        break;
-      }
+      else if (p.work)
+        atomicAdd(&p.work[threadIdx.x - 5], (unsigned long long)v);  // 2 nb, 3 flux, 4 sky
     }
   }
 }
