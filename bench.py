@@ -223,7 +223,7 @@ def main():
         with torch.cuda.stream(stream):
             vdist.all_reduce_words(t)
 
-    # per-ray work of this workload (same kernel; counters ride in registers)
+    # per-ray work of this workload (same kernels; counters ride in registers)
     os.environ["VR_COUNT_WORK"] = "1"
     cctx = capi.Context(local_rank)
     cctx.set_disks(xyzr, normals, nb_off, nb_idx)
@@ -236,8 +236,9 @@ def main():
     _, cinfo = cctx.flux_download()
     cctx.close()
     node_b, prim_b = bvh["node_bytes"], 32
-    bytes_per_ray = (work["node_visits"] * node_b + work["prim_tests"] * prim_b +
-                     work["nb_tests"] * (4 + 32) + work["flux_adds"] * 8) / (2.0 * count_rays)
+    per_ray = {k: v / (2.0 * count_rays) for k, v in work.items()}
+    trav_bytes_per_ray = per_ray["node_visits"] * node_b + per_ray["prim_tests"] * prim_b
+    bytes_per_ray = trav_bytes_per_ray + per_ray["nb_tests"] * (4 + 32) + per_ray["flux_adds"] * 8
 
     # warm-up
     for k in range(args.warmup):
@@ -270,15 +271,27 @@ def main():
     sampler.stop.set()
     sampler.join()
     elapsed_ms = ev0.elapsed_time(ev1)
-    last_kernel_ms = ctx.last_kernel_ms()  # trace kernels of the last step (both particles)
     _ = ctx.flux_download()
-    last_kernel_ms = ctx.last_kernel_ms()
     if world > 1:
         t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     rays_total = 2.0 * rays * world * args.steps
     value = rays_total / (elapsed_ms * 1e-3)
+
+    # the same steps once more with CUDA events around every kernel launch (on the
+    # launching stream), for the duration of the dominant kernel
+    phase = None
+    if rank == 0:
+        ctx.phase_timing(True)
+        for k in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            ctx.trace_device(src, parts, shard(args.warmup + k, rays))
+        phase = ctx.phase_ms()
+        ctx.phase_timing(False)
+    if world > 1:
+        dist.barrier()
 
     # end-to-end through the host C ABI: upload scene, build BVH, trace, read flux
     e2e_rays = rays
@@ -304,8 +317,20 @@ def main():
         return
 
     peak, peak_src = peaks()
-    kernel_rate = 2.0 * rays / (last_kernel_ms * 1e-3)  # rays/s inside the trace kernels
-    achieved = kernel_rate * bytes_per_ray / 1e9
+    # roofline of the dominant kernel (traverseKernel): algorithmic node + primitive
+    # bytes it fetched during the instrumented steps / its summed launch durations
+    trav_ms = phase["traverse_ms"]
+    trav_launches = max(phase["traverse_launches"], 1)
+    trav_bytes = trav_bytes_per_ray * 2.0 * rays * args.steps
+    achieved = trav_bytes / (trav_ms * 1e-3) / 1e9
+    traces_per_ray = sum(i.totalRaysTraced for i in cinfo) / (2.0 * count_rays)
+    traversals_per_launch = (traces_per_ray - per_ray["sky_finished"]) * 2.0 * rays * args.steps \
+        / trav_launches
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
     line = {
         "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -316,13 +341,29 @@ def main():
                 "what": "vr_scene_set_disks + vr_scene_commit (device BVH build) + vr_trace with "
                         "host buffers"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "bytes_per_ray": bytes_per_ray,
-                     "per_ray": {k: v / (2.0 * count_rays) for k, v in work.items()},
-                     "kernel_ms_per_step": last_kernel_ms,
-                     "note": "algorithmic bytes = counted node visits x %d B + primitive tests x "
-                             "32 B + neighbour tests x 36 B + flux adds x 8 B" % node_b},
+        "roofline": {
+            "kernel": "traverseKernel<0>", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak,
+            # DRAM bytes of an average launch: ncu's dram__bytes_{read,write}.sum per traversed
+            # slot (one --set full capture, profiles/traffic.json) x traversals per launch
+            "traffic": (traffic["traverse_dram_bytes_per_traversal"] * traversals_per_launch
+                        if traffic else None),
+            "traffic_source": traffic["source"] if traffic else None,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": trav_bytes / trav_launches,
+            "avg_launch_ms": trav_ms / trav_launches, "launches": trav_launches,
+            "kernel_share_of_step": trav_ms / max(trav_ms + phase["shade_ms"] + phase["other_ms"],
+                                                  1e-9),
+            "shade_ms_per_step": phase["shade_ms"] / args.steps,
+            "traverse_ms_per_step": trav_ms / args.steps,
+            "step": {"bytes_per_ray": bytes_per_ray,
+                     "achieved": value / world * bytes_per_ray / 1e9,
+                     "frac": value / world * bytes_per_ray / 1e9 / peak},
+            "per_ray": per_ray,
+            "note": "algorithmic bytes = counted node visits x %d B + primitive tests x 32 B for "
+                    "the traverse kernel (+ neighbour tests x 36 B + flux adds x 8 B for the whole "
+                    "step); the scene is L2-resident, so the HBM peak is a conservative "
+                    "denominator and DRAM traffic is far below the algorithmic bytes" % node_b},
         "clocks": sampler.summary(),
         "bvh": bvh, "neighbor_build_host_s": t_nb,
         "walk": {"traces_per_ray": [i.totalRaysTraced / count_rays for i in cinfo],

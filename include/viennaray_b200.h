@@ -169,6 +169,12 @@ int vr_debug_reflect(vr_ctx *ctx, int kind, int D, const float *rayDir, const fl
 /* acceleration-structure statistics: out[0] nodes, out[1] leaves, out[2]
  * max leaf size, out[3] node bytes, out[4] build ms (float bits) */
 int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out5);
+/* per-phase device time: with timing enabled every kernel launch of vr_trace*
+ * is bracketed by CUDA events on the context's stream; vr_debug_phase_ms
+ * returns the milliseconds and launch counts accumulated since it was enabled
+ * for {traverse kernel, shade kernel, everything else} */
+int vr_debug_phase_timing(vr_ctx *ctx, int enable);
+int vr_debug_phase_ms(vr_ctx *ctx, double *ms3, int64_t *launches3);
 /* per-ray traversal work counters of the last vr_trace* call when the
  * context was created with VR_COUNT_WORK=1 in the environment: out[0] node
  * visits, out[1] primitive tests, out[2] neighbour tests, out[3] flux adds,

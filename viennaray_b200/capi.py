@@ -21,7 +21,8 @@ EXPORTS = [
     "vr_trace_device", "vr_flux_device", "vr_flux_download", "vr_flux_download_fixed",
     "vr_ctx_stream", "vr_ctx_synchronize", "vr_last_kernel_ms", "vr_last_launch_count", "vr_build_neighbors", "vr_free",
     "vr_debug_intersect", "vr_debug_source_rays", "vr_debug_math", "vr_debug_philox",
-    "vr_debug_reflect", "vr_debug_bvh_stats", "vr_debug_work_counters",
+    "vr_debug_reflect", "vr_debug_bvh_stats", "vr_debug_work_counters", "vr_debug_phase_timing",
+    "vr_debug_phase_ms",
 ]
 
 
@@ -102,6 +103,8 @@ def lib():
                                        C.c_uint64, C.c_uint32, _vp]
         L.vr_debug_bvh_stats.argtypes = [_vp, _vp]
         L.vr_debug_work_counters.argtypes = [_vp, _vp]
+        L.vr_debug_phase_timing.argtypes = [_vp, C.c_int]
+        L.vr_debug_phase_ms.argtypes = [_vp, _vp, _vp]
         _lib = L
     return _lib
 
@@ -285,6 +288,16 @@ class Context:
         build_ms = np.array([out[4]], np.uint64).astype(np.uint32).view(np.float32)[0]
         return {"nodes": int(out[0]), "leaves": int(out[1]), "max_leaf": int(out[2]),
                 "node_bytes": int(out[3]), "build_ms": float(build_ms)}
+
+    def phase_timing(self, enable):
+        self._ck(self.L.vr_debug_phase_timing(self.h, 1 if enable else 0))
+
+    def phase_ms(self):
+        ms = np.zeros(3, np.float64)
+        n = np.zeros(3, np.int64)
+        self._ck(self.L.vr_debug_phase_ms(self.h, _p(ms), _p(n)))
+        return {"traverse_ms": float(ms[0]), "shade_ms": float(ms[1]), "other_ms": float(ms[2]),
+                "traverse_launches": int(n[0]), "shade_launches": int(n[1])}
 
     def work_counters(self):
         out = np.zeros(5, np.uint64)

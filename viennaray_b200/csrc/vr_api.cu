@@ -66,7 +66,8 @@ struct vr_ctx {
   bool timeKernels = false;  // VR_TIME_KERNELS=1: CUDA events around every launch
   std::vector<cudaEvent_t> tev;
   std::vector<int> tevKind;
-  double phaseMs[3] = {0, 0, 0};  // traverse, shade, other
+  double phaseMs[3] = {0, 0, 0};  // traverse, shade, other (accumulated)
+  long long phaseLaunches[3] = {0, 0, 0};
   uint32_t poolSlots = 1u << 24;
 };
 
@@ -193,11 +194,11 @@ static void collectMarks(vr_ctx *c) {
   if (!c->timeKernels || c->tev.empty())
     return;
   cudaEventSynchronize(c->tev.back());
-  c->phaseMs[0] = c->phaseMs[1] = c->phaseMs[2] = 0;
   for (size_t i = 1; i < c->tev.size(); ++i) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->tev[i - 1], c->tev[i]);
     c->phaseMs[c->tevKind[i]] += ms;
+    c->phaseLaunches[c->tevKind[i]] += 1;
   }
   for (auto e : c->tev)
     cudaEventDestroy(e);
@@ -723,10 +724,11 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
     CK(cudaEventSynchronize(ctx->ev1));
     CK(cudaEventElapsedTime(&ctx->lastMs, ctx->ev0, ctx->ev1));
   }
-  if (ctx->timeKernels) {
+  if (ctx->timeKernels && sync) {
     collectMarks(ctx);
-    fprintf(stderr, "[vr] phases: traverse %.3f ms, shade %.3f ms, other %.3f ms\n", ctx->phaseMs[0],
-            ctx->phaseMs[1], ctx->phaseMs[2]);
+    if (getenv("VR_TIME_KERNELS"))
+      fprintf(stderr, "[vr] phases (accumulated): traverse %.3f ms, shade %.3f ms, other %.3f ms\n",
+              ctx->phaseMs[0], ctx->phaseMs[1], ctx->phaseMs[2]);
   }
   return VR_OK;
 }
@@ -1050,6 +1052,31 @@ int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out5) {
   uint32_t bits;
   memcpy(&bits, &ctx->bvh.buildMs, 4);
   out5[4] = bits;
+  return VR_OK;
+}
+
+int vr_debug_phase_timing(vr_ctx *ctx, int enable) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  ctx->timeKernels = enable != 0;
+  for (int k = 0; k < 3; ++k) {
+    ctx->phaseMs[k] = 0;
+    ctx->phaseLaunches[k] = 0;
+  }
+  return VR_OK;
+}
+
+int vr_debug_phase_ms(vr_ctx *ctx, double *ms3, int64_t *launches3) {
+  if (!ctx || !ms3)
+    return VR_ERR_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  collectMarks(ctx);
+  for (int k = 0; k < 3; ++k) {
+    ms3[k] = ctx->phaseMs[k];
+    if (launches3)
+      launches3[k] = ctx->phaseLaunches[k];
+  }
   return VR_OK;
 }
 
