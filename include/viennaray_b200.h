@@ -129,6 +129,14 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *source, const vr_particle
 int vr_flux_device(vr_ctx *ctx, void **devicePtr, size_t *numWords);
 int vr_flux_download(vr_ctx *ctx, double *fluxOut, vr_trace_info *infoOut);
 int vr_flux_download_fixed(vr_ctx *ctx, uint64_t *fluxOut);
+/* Post-processing of the last trace on the device, float flux of one particle
+ * in the caller's primitive order: SOURCE normalisation
+ * flux[i] *= normFactor / areas[i] (rayTraceDisk.hpp:121-138,
+ * rayTraceTriangle.hpp:110-126; areas NULL = raw sums) followed, when smooth
+ * != 0 and the geometry is disks, by smoothFlux over the geometry's own
+ * neighbourhood (rayTraceDisk.hpp:146-193, numNeighbors == 1). */
+int vr_flux_postprocess(vr_ctx *ctx, int particle, const float *areas, float normFactor,
+                        int smooth, float *fluxOut);
 /* cudaStream_t of the context (for event timing by the caller) */
 void *vr_ctx_stream(vr_ctx *ctx);
 int vr_ctx_synchronize(vr_ctx *ctx);

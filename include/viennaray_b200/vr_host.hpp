@@ -901,6 +901,23 @@ public:
     }
   }
 
+  /// B200 addition: normalizeFlux(SOURCE) and smoothFlux(1) of the last apply()
+  /// computed on the device (vr_flux_postprocess); returns an empty vector on error.
+  [[nodiscard]] std::vector<NumericType> getDeviceFlux(bool normalize = true, bool smooth = true) {
+    std::vector<float> out(numPoints()), areas;
+    if (!this->ctx_ || !this->haveSource_)
+      return {};
+    if (normalize) {
+      computeDiskAreas();
+      areas.assign(diskAreas_.begin(), diskAreas_.end());
+    }
+    const float normFactor = static_cast<float>(this->sourceArea_) / static_cast<float>(this->totalRays());
+    if (vr_flux_postprocess(this->ctx_, 0, normalize ? areas.data() : nullptr, normFactor, smooth ? 1 : 0,
+                            out.data()) != VR_OK)
+      return {};
+    return std::vector<NumericType>(out.begin(), out.end());
+  }
+
   // introspection used by the parity tests (GeometryDisk getters)
   [[nodiscard]] std::size_t numPoints() const { return xyzr_.size() / 4; }
   [[nodiscard]] const std::vector<double> &getDiskAreas() {

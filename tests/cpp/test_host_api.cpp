@@ -244,6 +244,15 @@ static void testTraceInterface(const std::string &out) {
   VC_TEST_ASSERT(info.geometryHits > 0 && info.nonGeometryHits > 0);
   auto flux = rayTracer.getLocalData().getVectorData("hitFlux");
   dump(out + "/traceInterface_raw.f32", flux);
+  {  // device post-processing == host post-processing (normalise + smooth over 1 ring)
+    auto hostFlux = flux;
+    rayTracer.normalizeFlux(hostFlux);
+    rayTracer.smoothFlux(hostFlux, 1);
+    auto devFlux = rayTracer.getDeviceFlux(true, true);
+    VC_TEST_ASSERT(devFlux.size() == hostFlux.size());
+    for (std::size_t i = 0; i < devFlux.size(); ++i)
+      VC_TEST_ASSERT_ISCLOSE(devFlux[i], hostFlux[i], 1e-5 * (1 + std::fabs(hostFlux[i])));
+  }
   rayTracer.normalizeFlux(flux);
   rayTracer.smoothFlux(flux, 2);
   double mean = 0;

@@ -198,3 +198,29 @@ def test_multi_particle_label_major(pair):
         fo, io = orc.trace(po.Particle(p.kind, p.sticking, p.sourcePower, p.coneMinAngle), oc)
         assert (f[k] == fo / po.FLUX_SCALE).all()
         assert infos[k].geometryHits == io.geoHits
+
+
+def test_flux_postprocess_on_device(pair):
+    """normalizeFlux(SOURCE) + smoothFlux(1) on the device against the oracle's
+    float restatement of rayTraceDisk.hpp:103-193, bit for bit."""
+    c, orc, ctx, src, st = pair
+    num = 80000
+    ctx.trace_device(src, [common.gpu_particle(c)], host.config(num, SEED), sync=True)
+    fo, _ = orc.trace(common.oracle_particle(c), orc.config(num, SEED))
+    raw = (fo / po.FLUX_SCALE).astype(np.float32)
+    assert (ctx.flux_postprocess() == raw).all()
+    rng = np.random.default_rng(5)
+    areas = (0.5 + rng.random(orc.n)).astype(np.float32)
+    lo, hi = st["bbox"]
+    _, first, second, _, _ = host.trace_settings(c["source_dir"])
+    area = np.float32(hi[first] - lo[first])
+    if c["D"] == 3:
+        area = np.float32(area * np.float32(hi[second] - lo[second]))
+    norm = np.float32(area / np.float32(num))
+    expect = orc.normalize_flux_source(raw, areas, num)
+    got = ctx.flux_postprocess(0, areas, norm, smooth=False)
+    assert (got.view(np.uint32) == expect.view(np.uint32)).all()
+    got = ctx.flux_postprocess(0, areas, norm, smooth=True)
+    if c["geo"] == "disk":
+        expect = orc.smooth_flux(expect)
+    assert (got.view(np.uint32) == expect.view(np.uint32)).all()

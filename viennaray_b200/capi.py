@@ -19,6 +19,7 @@ EXPORTS = [
     "vr_ctx_create", "vr_ctx_destroy", "vr_last_error", "vr_scene_set_disks",
     "vr_scene_set_triangles", "vr_scene_set_boundary", "vr_scene_commit", "vr_trace",
     "vr_trace_device", "vr_flux_device", "vr_flux_download", "vr_flux_download_fixed",
+    "vr_flux_postprocess",
     "vr_ctx_stream", "vr_ctx_synchronize", "vr_last_kernel_ms", "vr_last_launch_count", "vr_build_neighbors", "vr_free",
     "vr_debug_intersect", "vr_debug_source_rays", "vr_debug_math", "vr_debug_philox",
     "vr_debug_reflect", "vr_debug_bvh_stats", "vr_debug_work_counters", "vr_debug_phase_timing",
@@ -85,6 +86,7 @@ def lib():
         L.vr_flux_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]
         L.vr_flux_download.argtypes = [_vp, _vp, _vp]
         L.vr_flux_download_fixed.argtypes = [_vp, _vp]
+        L.vr_flux_postprocess.argtypes = [_vp, C.c_int, _vp, C.c_float, C.c_int, _vp]
         L.vr_ctx_stream.restype = _vp
         L.vr_ctx_stream.argtypes = [_vp]
         L.vr_ctx_synchronize.argtypes = [_vp]
@@ -230,6 +232,15 @@ class Context:
         flux = np.zeros((self.num_particles, self.n), np.uint64)
         self._ck(self.L.vr_flux_download_fixed(self.h, _p(flux)))
         return flux
+
+    def flux_postprocess(self, particle=0, areas=None, norm_factor=1.0, smooth=False):
+        """Normalised / smoothed float flux of one particle, computed on the device."""
+        if areas is not None:
+            areas = np.ascontiguousarray(areas, np.float32)
+        out = np.zeros(self.n, np.float32)
+        self._ck(self.L.vr_flux_postprocess(self.h, particle, _p(areas), np.float32(norm_factor),
+                                            1 if smooth else 0, _p(out)))
+        return out
 
     def stream(self):
         return self.L.vr_ctx_stream(self.h)

@@ -791,6 +791,36 @@ int vr_flux_download(vr_ctx *ctx, double *fluxOut, vr_trace_info *infoOut) {
   return VR_OK;
 }
 
+int vr_flux_postprocess(vr_ctx *ctx, int particle, const float *areas, float normFactor,
+                        int smooth, float *fluxOut) {
+  if (!ctx || !fluxOut)
+    return VR_ERR_ARGUMENT;
+  if (!ctx->dResult || !ctx->committed)
+    return fail(ctx, VR_ERR_STATE, "vr_flux_postprocess: no trace has run");
+  if (particle < 0 || particle >= ctx->numParticles)
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_flux_postprocess: particle index out of range");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = ctx->n;
+  float *buf = nullptr;  // areas | tmpA | tmpB | out
+  CK(cudaMallocAsync(&buf, sizeof(float) * 4 * n, ctx->stream));
+  cudaError_t e = cudaSuccess;
+  if (areas)
+    e = cudaMemcpyAsync(buf, areas, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = postprocessFlux(ctx->scene, ctx->dResult + (size_t)particle * n, ctx->bvh.sortedToOrig,
+                        areas ? buf : nullptr, normFactor, smooth, buf + n, buf + 2 * n,
+                        buf + 3 * n, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(fluxOut, buf + 3 * n, sizeof(float) * n, cudaMemcpyDeviceToHost,
+                        ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  cudaFreeAsync(buf, ctx->stream);
+  if (e != cudaSuccess)
+    return failCuda(ctx, e, "vr_flux_postprocess");
+  return VR_OK;
+}
+
 int vr_flux_download_fixed(vr_ctx *ctx, uint64_t *fluxOut) {
   if (!ctx || !fluxOut)
     return VR_ERR_ARGUMENT;

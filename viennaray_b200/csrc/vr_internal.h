@@ -115,6 +115,12 @@ cudaError_t remapNeighbors(const uint32_t *s2o, const uint32_t *offO, const uint
                            uint32_t n, uint32_t *o2s, uint32_t *cnt, uint32_t *off, uint32_t *idx,
                            cudaStream_t s);
 
+// flux of one particle: fixed point (internal order) -> float, optional SOURCE
+// normalisation by areas[original id], optional neighbour smoothing, original order
+cudaError_t postprocessFlux(const DeviceScene &sc, const unsigned long long *fixed,
+                            const uint32_t *s2o, const float *areas, float normFactor, int smooth,
+                            float *tmpA, float *tmpB, float *outOrig, cudaStream_t s);
+
 // sky map for rays that travel towards the source (see DeviceScene::sky).
 // table: G*G float2, device.  top: host out.
 cudaError_t buildSky(const DeviceScene &sc, int G, int upAxis, float upSign, int axisA, int axisB,

@@ -224,7 +224,61 @@ __global__ void skySlopeKernel(const unsigned int *hMax, const unsigned int *hMi
 
 __global__ void skyTopKernel(unsigned int *top) { *top = __float_as_uint(o2f(*top)); }
 
+// ---- flux post-processing (rayTraceDisk.hpp:103-193, rayTraceTriangle.hpp:92-130) ----
+// internal (BVH) order in, float out.  f = (float)(fixed / 2^30); SOURCE
+// normalisation: f *= normFactor / area[original id]
+__global__ void fluxToFloatKernel(const unsigned long long *fixed, const uint32_t *s2o,
+                                  const float *areas, float normFactor, uint32_t n, float *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  float f = (float)((double)fixed[i] * (1.0 / 1073741824.0));
+  if (areas)
+    f *= normFactor / areas[s2o[i]];
+  out[i] = f;
+}
+
+// smoothFlux with the geometry's own neighbourhood: value and weights in the
+// CSR row order of the caller's lists
+__global__ void smoothFluxKernel(DeviceScene sc, const float *in, float *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sc.numPrims)
+    return;
+  const float4 ni = sc.prim[2 * i + 1];
+  float vv = in[i], sum = 1.f;
+  for (uint32_t k = sc.nbOff[i]; k < sc.nbOff[i + 1]; ++k) {
+    const uint32_t j = sc.nbIdx[k];
+    const float4 nj = sc.prim[2 * j + 1];
+    const float w = (ni.x * nj.x + ni.y * nj.y) + ni.z * nj.z;
+    if (w > 0.f) {
+      vv += in[j] * w;
+      sum += w;
+    }
+  }
+  out[i] = vv / sum;
+}
+
+__global__ void unsortFloatKernel(const float *src, const uint32_t *s2o, uint32_t n, float *dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    dst[s2o[i]] = src[i];
+}
+
 }  // namespace
+
+cudaError_t postprocessFlux(const DeviceScene &sc, const unsigned long long *fixed,
+                            const uint32_t *s2o, const float *areas, float normFactor, int smooth,
+                            float *tmpA, float *tmpB, float *outOrig, cudaStream_t s) {
+  const uint32_t n = sc.numPrims;
+  fluxToFloatKernel<<<(n + 255) / 256, 256, 0, s>>>(fixed, s2o, areas, normFactor, n, tmpA);
+  const float *cur = tmpA;
+  if (smooth && sc.geoType == 0) {
+    smoothFluxKernel<<<(n + 255) / 256, 256, 0, s>>>(sc, tmpA, tmpB);
+    cur = tmpB;
+  }
+  unsortFloatKernel<<<(n + 255) / 256, 256, 0, s>>>(cur, s2o, n, outOrig);
+  return cudaGetLastError();
+}
 
 cudaError_t buildSky(const DeviceScene &sc, int G, int upAxis, float upSign, int axisA, int axisB,
                      const float lo[2], const float hi[2], float2 *table, float *topOut,
