@@ -60,6 +60,15 @@ int vr_scene_set_disks(vr_ctx *ctx, const float *xyzr, const float *nxyz, uint32
                        const int32_t *materialIds, const uint32_t *nbOffsets,
                        const uint32_t *nbIndices);
 
+/* Neighbour lists built on the device for the disks set before (pass NULL
+ * lists to vr_scene_set_disks): replaces PointNeighborhood::init
+ * (rayPointNeighborhood.hpp:43-107,287-298) with the semantics of
+ * vr_build_neighbors.  points: N x 3, the coordinates as given by the caller
+ * (rayGeometryDisk.hpp:191).  vr_scene_get_neighbors returns malloc'ed copies
+ * (release with vr_free). */
+int vr_scene_build_neighbors(vr_ctx *ctx, int D, const float *points, float distance);
+int vr_scene_get_neighbors(vr_ctx *ctx, uint32_t **offsetsOut, uint32_t **indicesOut);
+
 /* Triangle geometry; replaces GeometryTriangle::initGeometry
  * (rayGeometryTriangle.hpp:15-92,246-254).  normals: N x 3 unit normals. */
 int vr_scene_set_triangles(vr_ctx *ctx, const float *vertices, uint32_t numVertices,

@@ -224,3 +224,29 @@ def test_flux_postprocess_on_device(pair):
     if c["geo"] == "disk":
         expect = orc.smooth_flux(expect)
     assert (got.view(np.uint32) == expect.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("name", ["disk3D", "disk2D", "trench", "holes", "plane"])
+def test_neighbor_build_on_device(name):
+    """PointNeighborhood on the device == host build == oracle, and a trace
+    through device-built lists gives the same flux words."""
+    c = common.case(name)
+    orc = common.make_oracle(c)
+    st = common.product_setup(c)
+    ctx = capi.Context(0)
+    ctx.set_disks(st["xyzr"], st["normals"])  # no lists
+    r = host.disk_radius(c["grid_delta"], c["D"])
+    ctx.build_neighbors_device(c["D"], c["points"], np.float32(2) * r)
+    off, idx = ctx.get_neighbors()
+    off_o, idx_o = orc.neighbors()
+    assert (off == off_o).all() and (idx == idx_o).all()
+    lo, hi = st["bbox"]
+    _, first, second, _, _ = host.trace_settings(c["source_dir"])
+    cond2 = c["bc"][second] if c["D"] == 3 else capi.BOUNDARY_IGNORE
+    ctx.set_boundary(lo, hi, first, second, c["bc"][first], cond2, c["D"])
+    ctx.commit()
+    src = host.source_desc(lo, hi, c["source_dir"])
+    ctx.trace_device(src, [common.gpu_particle(c)], host.config(60000, SEED), sync=True)
+    fo, _ = orc.trace(common.oracle_particle(c), orc.config(60000, SEED))
+    assert (ctx.flux_download_fixed()[0] == fo).all()
+    ctx.close()

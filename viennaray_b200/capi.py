@@ -17,7 +17,8 @@ BOUNDARY_REFLECTIVE, BOUNDARY_PERIODIC, BOUNDARY_IGNORE = 0, 1, 2
 
 EXPORTS = [
     "vr_ctx_create", "vr_ctx_destroy", "vr_last_error", "vr_scene_set_disks",
-    "vr_scene_set_triangles", "vr_scene_set_boundary", "vr_scene_commit", "vr_trace",
+    "vr_scene_set_triangles", "vr_scene_build_neighbors", "vr_scene_get_neighbors",
+    "vr_scene_set_boundary", "vr_scene_commit", "vr_trace",
     "vr_trace_device", "vr_flux_device", "vr_flux_download", "vr_flux_download_fixed",
     "vr_flux_postprocess",
     "vr_ctx_stream", "vr_ctx_synchronize", "vr_last_kernel_ms", "vr_last_launch_count", "vr_build_neighbors", "vr_free",
@@ -81,6 +82,8 @@ def lib():
         L.vr_scene_set_boundary.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int]
         L.vr_scene_commit.argtypes = [_vp]
+        L.vr_scene_build_neighbors.argtypes = [_vp, C.c_int, _vp, C.c_float]
+        L.vr_scene_get_neighbors.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp)]
         L.vr_trace.argtypes = [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp]
         L.vr_trace_device.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int]
         L.vr_flux_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]
@@ -172,6 +175,23 @@ class Context:
         self.n = len(xyzr)
         self._ck(self.L.vr_scene_set_disks(self.h, _p(xyzr), _p(normals), self.n,
                                            _p(material_ids), _p(nb_offsets), _p(nb_indices)))
+
+    def build_neighbors_device(self, D, points, distance):
+        """Neighbour lists of the disks set before, built on the device."""
+        points = np.ascontiguousarray(points, np.float32)
+        assert points.shape == (self.n, 3)
+        self._ck(self.L.vr_scene_build_neighbors(self.h, D, _p(points), np.float32(distance)))
+
+    def get_neighbors(self):
+        off, idx = _vp(), _vp()
+        self._ck(self.L.vr_scene_get_neighbors(self.h, C.byref(off), C.byref(idx)))
+        offsets = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_uint32)), (self.n + 1,)).copy()
+        total = int(offsets[-1])
+        indices = (np.ctypeslib.as_array(C.cast(idx, C.POINTER(C.c_uint32)), (total,)).copy()
+                   if total else np.zeros(0, np.uint32))
+        self.L.vr_free(off)
+        self.L.vr_free(idx)
+        return offsets, indices
 
     def set_triangles(self, verts, tris, normals, material_ids=None):
         verts = np.ascontiguousarray(verts, np.float32)

@@ -424,6 +424,64 @@ int vr_scene_set_triangles(vr_ctx *ctx, const float *verts, uint32_t nVerts, con
   return VR_OK;
 }
 
+int vr_scene_build_neighbors(vr_ctx *ctx, int D, const float *points, float distance) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  if (!points || (D != 2 && D != 3) || !(distance > 0.f))
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_build_neighbors: invalid argument");
+  if (ctx->geoType != 0 || ctx->n == 0)
+    return fail(ctx, VR_ERR_STATE, "vr_scene_build_neighbors: set the disks first");
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t n = ctx->n;
+  float lo[3] = {INFINITY, INFINITY, INFINITY};
+  for (uint32_t i = 0; i < n; ++i)
+    for (int a = 0; a < D; ++a)
+      lo[a] = std::min(lo[a], points[3 * (size_t)i + a]);
+  ctx->committed = false;
+  cudaFreeAsync(ctx->dNbOffO, ctx->stream);
+  cudaFreeAsync(ctx->dNbIdxO, ctx->stream);
+  ctx->dNbOffO = ctx->dNbIdxO = nullptr;
+  ctx->nbTotal = 0;
+  float *dPts = nullptr;
+  CK(uploadArray(ctx, &dPts, points, (size_t)3 * n));
+  cudaError_t e = cudaMallocAsync(&ctx->dNbOffO, sizeof(uint32_t) * ((size_t)n + 1), ctx->stream);
+  if (e == cudaSuccess)
+    e = buildNeighborsDevice(D, dPts, n, lo, distance, ctx->dNbOffO, &ctx->dNbIdxO, &ctx->nbTotal,
+                             ctx->stream);
+  cudaFreeAsync(dPts, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess)
+    return failCuda(ctx, e, "vr_scene_build_neighbors");
+  return VR_OK;
+}
+
+int vr_scene_get_neighbors(vr_ctx *ctx, uint32_t **offsetsOut, uint32_t **indicesOut) {
+  if (!ctx || !offsetsOut || !indicesOut)
+    return VR_ERR_ARGUMENT;
+  if (ctx->geoType != 0 || !ctx->dNbOffO)
+    return fail(ctx, VR_ERR_STATE, "vr_scene_get_neighbors: no neighbour lists on the device");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = ctx->n;
+  uint32_t *off = (uint32_t *)malloc(sizeof(uint32_t) * (n + 1));
+  uint32_t *idx = (uint32_t *)malloc(sizeof(uint32_t) * std::max<size_t>(ctx->nbTotal, 1));
+  cudaError_t e = cudaMemcpyAsync(off, ctx->dNbOffO, sizeof(uint32_t) * (n + 1),
+                                  cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && ctx->nbTotal)
+    e = cudaMemcpyAsync(idx, ctx->dNbIdxO, sizeof(uint32_t) * ctx->nbTotal, cudaMemcpyDeviceToHost,
+                        ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    free(off);
+    free(idx);
+    return failCuda(ctx, e, "vr_scene_get_neighbors");
+  }
+  *offsetsOut = off;
+  *indicesOut = idx;
+  return VR_OK;
+}
+
 int vr_scene_set_boundary(vr_ctx *ctx, const float bboxMin[3], const float bboxMax[3],
                           int firstDir, int secondDir, int condFirst, int condSecond, int D) {
   if (!ctx)

@@ -115,6 +115,10 @@ cudaError_t remapNeighbors(const uint32_t *s2o, const uint32_t *offO, const uint
                            uint32_t n, uint32_t *o2s, uint32_t *cnt, uint32_t *off, uint32_t *idx,
                            cudaStream_t s);
 
+cudaError_t buildNeighborsDevice(int D, const float *pts, uint32_t n, const float lo[3],
+                                 float distance, uint32_t *offOut, uint32_t **idxOut,
+                                 size_t *totalOut, cudaStream_t s);
+
 // flux of one particle: fixed point (internal order) -> float, optional SOURCE
 // normalisation by areas[original id], optional neighbour smoothing, original order
 cudaError_t postprocessFlux(const DeviceScene &sc, const unsigned long long *fixed,

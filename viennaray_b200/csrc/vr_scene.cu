@@ -4,6 +4,7 @@
 // all run as kernels, so vr_scene_commit moves no primitive data through host
 // loops.  Replaces what GeometryDisk / GeometryTriangle::initGeometry hand to
 // Embree (rayGeometryDisk.hpp:102-193, rayGeometryTriangle.hpp:15-92).
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <cstring>
@@ -224,6 +225,91 @@ __global__ void skySlopeKernel(const unsigned int *hMax, const unsigned int *hMi
 
 __global__ void skyTopKernel(unsigned int *top) { *top = __float_as_uint(o2f(*top)); }
 
+// ---- neighbour lists on the device (PointNeighborhood::init, rayPointNeighborhood.hpp:43-107,
+// 287-298): uniform grid of cell size >= distance over the first D axes, points
+// sorted by cell key; every point scans the 3 x 3 (x 3) block of cells around it.
+__device__ __forceinline__ unsigned long long cellKey(long long x, long long y, long long z) {
+  return ((unsigned long long)x & 0x1fffffull) | (((unsigned long long)y & 0x1fffffull) << 21) |
+         (((unsigned long long)z & 0x1fffffull) << 42);
+}
+__device__ __forceinline__ long long cellOf(const float *p, int a, int D, const float *lo,
+                                            float cell) {
+  return a < D ? (long long)floorf((p[a] - lo[a]) / cell) + 1 : 1;
+}
+struct NbGrid {
+  int D;
+  float lo[3], cell, dist, dist2;
+};
+
+__global__ void nbKeysKernel(const float *pts, uint32_t n, NbGrid g, unsigned long long *keys,
+                             uint32_t *vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float *p = pts + 3 * (size_t)i;
+  keys[i] = cellKey(cellOf(p, 0, g.D, g.lo, g.cell), cellOf(p, 1, g.D, g.lo, g.cell),
+                    cellOf(p, 2, g.D, g.lo, g.cell));
+  vals[i] = i;
+}
+
+__device__ __forceinline__ bool isNeighbor(const float *p, const float *q, const NbGrid &g) {
+  for (int a = 0; a < g.D; ++a)
+    if (fabsf(p[a] - q[a]) > g.dist)
+      return false;
+  const float dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+  return (dx * dx + dy * dy) + dz * dz <= g.dist2;
+}
+
+// FILL == false: cnt[i] = number of neighbours; FILL == true: rows written and sorted
+template <bool FILL>
+__global__ void nbScanKernel(const float *pts, uint32_t n, NbGrid g, const unsigned long long *keys,
+                             const uint32_t *vals, uint32_t *cnt, const uint32_t *off,
+                             uint32_t *idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float *p = pts + 3 * (size_t)i;
+  const long long cx = cellOf(p, 0, g.D, g.lo, g.cell), cy = cellOf(p, 1, g.D, g.lo, g.cell),
+                  cz = cellOf(p, 2, g.D, g.lo, g.cell);
+  const int zr = g.D == 3 ? 1 : 0;
+  uint32_t c = 0;
+  const uint32_t base = FILL ? off[i] : 0u;
+  for (int dz = -zr; dz <= zr; ++dz)
+    for (int dy = -1; dy <= 1; ++dy) {
+      const unsigned long long k0 = cellKey(cx - 1, cy + dy, cz + dz),
+                               k1 = cellKey(cx + 1, cy + dy, cz + dz);
+      uint32_t a = 0, b = n;  // first key >= k0
+      while (a < b) {
+        const uint32_t m = (a + b) >> 1;
+        if (keys[m] < k0)
+          a = m + 1;
+        else
+          b = m;
+      }
+      for (; a < n && keys[a] <= k1; ++a) {
+        const uint32_t j = vals[a];
+        if (j != i && isNeighbor(p, pts + 3 * (size_t)j, g)) {
+          if (FILL)
+            idx[base + c] = j;
+          ++c;
+        }
+      }
+    }
+  if (!FILL) {
+    cnt[i] = c;
+    return;
+  }
+  for (uint32_t u = 1; u < c; ++u) {  // rows ascending, like the host lists
+    const uint32_t v = idx[base + u];
+    uint32_t w = u;
+    while (w > 0 && idx[base + w - 1] > v) {
+      idx[base + w] = idx[base + w - 1];
+      --w;
+    }
+    idx[base + w] = v;
+  }
+}
+
 // ---- flux post-processing (rayTraceDisk.hpp:103-193, rayTraceTriangle.hpp:92-130) ----
 // internal (BVH) order in, float out.  f = (float)(fixed / 2^30); SOURCE
 // normalisation: f *= normFactor / area[original id]
@@ -265,6 +351,67 @@ __global__ void unsortFloatKernel(const float *src, const uint32_t *s2o, uint32_
 }
 
 }  // namespace
+
+// Neighbour CSR (original indices) of n points (device, n x 3).  offOut: n+1
+// words allocated by the caller; idxOut / totalOut: allocated here (stream-ordered).
+cudaError_t buildNeighborsDevice(int D, const float *pts, uint32_t n, const float lo[3],
+                                 float distance, uint32_t *offOut, uint32_t **idxOut,
+                                 size_t *totalOut, cudaStream_t s) {
+  NbGrid g;
+  g.D = D;
+  for (int a = 0; a < 3; ++a)
+    g.lo[a] = lo[a];
+  g.cell = distance * 1.0001f;
+  g.dist = distance;
+  g.dist2 = distance * distance;
+  unsigned long long *keys = nullptr, *keysS = nullptr;
+  uint32_t *vals = nullptr, *valsS = nullptr, *cnt = nullptr;
+  void *tmp = nullptr;
+  *idxOut = nullptr;
+  *totalOut = 0;
+  auto cleanup = [&]() {
+    cudaFreeAsync(keys, s);
+    cudaFreeAsync(keysS, s);
+    cudaFreeAsync(vals, s);
+    cudaFreeAsync(valsS, s);
+    cudaFreeAsync(cnt, s);
+    cudaFreeAsync(tmp, s);
+  };
+#define NB_CK(x)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) {                                                                       \
+      cleanup();                                                                                   \
+      return e_;                                                                                   \
+    }                                                                                              \
+  } while (0)
+  NB_CK(cudaMallocAsync(&keys, sizeof(unsigned long long) * n, s));
+  NB_CK(cudaMallocAsync(&keysS, sizeof(unsigned long long) * n, s));
+  NB_CK(cudaMallocAsync(&vals, sizeof(uint32_t) * n, s));
+  NB_CK(cudaMallocAsync(&valsS, sizeof(uint32_t) * n, s));
+  NB_CK(cudaMallocAsync(&cnt, sizeof(uint32_t) * n, s));
+  const unsigned grid = (n + 255) / 256;
+  nbKeysKernel<<<grid, 256, 0, s>>>(pts, n, g, keys, vals);
+  size_t bytes = 0, bytes2 = 0;
+  NB_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keysS, vals, valsS, (int)n, 0, 63, s));
+  NB_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes2, cnt, offOut, (int)n, s));
+  bytes = bytes > bytes2 ? bytes : bytes2;
+  NB_CK(cudaMallocAsync(&tmp, bytes ? bytes : 16, s));
+  NB_CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys, keysS, vals, valsS, (int)n, 0, 63, s));
+  nbScanKernel<false><<<grid, 256, 0, s>>>(pts, n, g, keysS, valsS, cnt, nullptr, nullptr);
+  NB_CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, cnt, offOut, (int)n, s));
+  closeOffsetsKernel<<<1, 1, 0, s>>>(cnt, n, offOut);
+  uint32_t total = 0;
+  NB_CK(cudaMemcpyAsync(&total, offOut + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  NB_CK(cudaStreamSynchronize(s));
+  NB_CK(cudaMallocAsync(idxOut, sizeof(uint32_t) * (total ? total : 1), s));
+  nbScanKernel<true><<<grid, 256, 0, s>>>(pts, n, g, keysS, valsS, nullptr, offOut, *idxOut);
+  NB_CK(cudaGetLastError());
+#undef NB_CK
+  *totalOut = total;
+  cleanup();
+  return cudaSuccess;
+}
 
 cudaError_t postprocessFlux(const DeviceScene &sc, const unsigned long long *fixed,
                             const uint32_t *s2o, const float *areas, float normFactor, int smooth,
