@@ -79,6 +79,16 @@ __device__ __forceinline__ void philox4x32(uint32_t k0, uint32_t k1, uint32_t c0
   out[3] = c3;
 }
 
+// one block of the stream, as a real call (values in registers both ways): the
+// generator is used at a dozen call sites of the shade kernel and ten inlined
+// Philox rounds per site bloat it beyond the instruction cache
+__device__ __noinline__ uint4 philoxBlock(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                          uint32_t blk) {
+  uint32_t o[4];
+  philox4x32(k0, k1, c0, c1, blk, 0u, o);
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // Per-ray stream; replaces RNG rngState(tea<3>(idx, seed)),
 // rayTraceKernel.hpp:120-121.  The four-word buffer is shifted instead of
 // indexed so it stays in registers.
@@ -112,12 +122,11 @@ struct Rng {
   }
   __device__ __forceinline__ uint32_t u32() {
     if (left == 0) {
-      uint32_t o[4];
-      philox4x32(k0, k1, c0, c1, blk, 0u, o);
-      b0 = o[0];
-      b1 = o[1];
-      b2 = o[2];
-      b3 = o[3];
+      const uint4 o = philoxBlock(k0, k1, c0, c1, blk);
+      b0 = o.x;
+      b1 = o.y;
+      b2 = o.z;
+      b3 = o.w;
       ++blk;
       left = 4;
     }
