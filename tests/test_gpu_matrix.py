@@ -1,0 +1,114 @@
+"""-m gpu: the option matrix of the hot path against the oracle, bit for bit --
+all six source directions, every pairing of boundary conditions, the three
+device particles, tilted primary directions, the hit-count limits
+(maxReflections / maxBoundaryHits, rayTraceKernel.hpp:207-211,320-324) and the
+2D path, on small scenes (a trench turned towards each source side)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests import common
+from viennaray_b200 import capi, host, scenes
+
+pytestmark = pytest.mark.gpu
+SEED = 991
+PARTICLES = {"diffuse": (0, 0.3, 1.0, 0.0), "specular": (1, 0.5, 5.0, 0.0),
+             "coned": (2, 0.5, 50.0, float(np.deg2rad(80.0)))}
+
+
+def turned_trench(source_dir):
+    """The reduced C4 trench with its opening turned towards the given source side."""
+    p, n, gd = scenes.trench(num_slices=24, half_width=5, depth=14, half_extent=16)
+    axis, first, second, min_max, _ = host.trace_settings(source_dir)
+    sign = 1.0 if min_max else -1.0
+    pts = np.zeros_like(p)
+    nrm = np.zeros_like(n)
+    # trench frame: x along the trench, y across, z up  ->  first, second, source axis
+    pts[:, first], pts[:, second], pts[:, axis] = p[:, 0], p[:, 1], sign * p[:, 2]
+    nrm[:, first], nrm[:, second], nrm[:, axis] = n[:, 0], n[:, 1], sign * n[:, 2]
+    return np.ascontiguousarray(pts), np.ascontiguousarray(nrm), gd
+
+
+def run_pair(c, num, max_refl=0xFFFFFFFF, max_bhits=1000, primary_dir=None):
+    orc = common.make_oracle(c)
+    ctx, src, _ = common.make_gpu(c, primary_dir=primary_dir)
+    fo, io = orc.trace(common.oracle_particle(c),
+                       orc.config(num, SEED, max_reflections=max_refl, max_boundary_hits=max_bhits,
+                                  primary_dir=primary_dir))
+    ctx.trace_device(src, [common.gpu_particle(c)],
+                     host.config(num, SEED, max_reflections=max_refl, max_boundary_hits=max_bhits),
+                     sync=True)
+    fg = ctx.flux_download_fixed()[0]
+    ig = ctx.flux_download()[1][0]
+    ctx.close()
+    d = io.as_dict()
+    assert (fg == fo).all(), "%d primitives differ" % int((fg != fo).sum())
+    assert (ig.totalRaysTraced, ig.geometryHits, ig.nonGeometryHits, ig.boundaryHits,
+            ig.reflections, ig.raysTerminated) == \
+        (d["totalTraces"], d["geoHits"], d["nonGeoHits"], d["boundaryHits"], d["reflections"],
+         d["raysTerminated"])
+    return d
+
+
+@pytest.mark.parametrize("source_dir", range(6))
+@pytest.mark.parametrize("bc_pair", list(itertools.product(range(3), repeat=2)))
+def test_source_sides_and_boundary_conditions(source_dir, bc_pair):
+    pts, nrm, gd = turned_trench(source_dir)
+    _, first, second, _, _ = host.trace_settings(source_dir)
+    bc = [2, 2, 2]
+    bc[first], bc[second] = bc_pair
+    kind, st, pw, cone = PARTICLES[("diffuse", "specular", "coned")[(source_dir + bc_pair[0]) % 3]]
+    c = dict(name="turned", D=3, geo="disk", points=pts, normals=nrm, grid_delta=gd, bc=bc,
+             source_dir=source_dir, kind=kind, sticking=st, power=pw, cone=cone)
+    d = run_pair(c, 60000)
+    assert d["geoHits"] > 0
+
+
+@pytest.mark.parametrize("pname", list(PARTICLES))
+@pytest.mark.parametrize("primary", [(0.3, 0.2, -1.0), (-0.6, 0.0, -0.8)])
+def test_tilted_primary_direction(pname, primary):
+    pts, nrm, gd = turned_trench(host.POS_Z)
+    kind, st, pw, cone = PARTICLES[pname]
+    c = dict(name="tilted", D=3, geo="disk", points=pts, normals=nrm, grid_delta=gd, bc=[1, 0, 2],
+             source_dir=host.POS_Z, kind=kind, sticking=st, power=pw, cone=cone)
+    run_pair(c, 60000, primary_dir=np.asarray(primary, np.float32))
+
+
+@pytest.mark.parametrize("max_refl,max_bhits", [(0, 1000), (1, 1000), (3, 2), (0xFFFFFFFF, 0),
+                                                (0xFFFFFFFF, 1)])
+def test_hit_count_limits(max_refl, max_bhits):
+    pts, nrm, gd = turned_trench(host.POS_Z)
+    c = dict(name="limits", D=3, geo="disk", points=pts, normals=nrm, grid_delta=gd, bc=[0, 1, 2],
+             source_dir=host.POS_Z, kind=0, sticking=0.05, power=1.0, cone=0.0)
+    d = run_pair(c, 60000, max_refl=max_refl, max_bhits=max_bhits)
+    if max_refl < 10:
+        assert d["raysTerminated"] > 0
+
+
+@pytest.mark.parametrize("source_dir", [host.POS_X, host.NEG_X, host.POS_Y, host.NEG_Y])
+@pytest.mark.parametrize("cond", range(3))
+def test_2d_sources_and_boundaries(source_dir, cond):
+    c0 = common.case("disk2D")  # trench profile in x-y, opening towards +y
+    pts, nrm = c0["points"].copy(), c0["normals"].copy()
+    axis, first, _, min_max, _ = host.trace_settings(source_dir)
+    sign = 1.0 if min_max else -1.0
+    p2, n2 = np.zeros_like(pts), np.zeros_like(nrm)
+    p2[:, first], p2[:, axis] = pts[:, 0], sign * pts[:, 1]
+    n2[:, first], n2[:, axis] = nrm[:, 0], sign * nrm[:, 1]
+    bc = [2, 2, 2]
+    bc[first] = cond
+    c = dict(c0, points=np.ascontiguousarray(p2), normals=np.ascontiguousarray(n2), bc=bc,
+             source_dir=source_dir, kind=(0, 2, 1)[cond], sticking=0.2, power=(1.0, 20.0, 3.0)[cond],
+             cone=float(np.deg2rad(70.0)))
+    run_pair(c, 40000)
+
+
+@pytest.mark.parametrize("bc_pair", [(0, 0), (1, 1), (2, 2), (0, 1)])
+@pytest.mark.parametrize("pname", list(PARTICLES))
+def test_triangles_matrix(bc_pair, pname):
+    c = common.case("triangle3D")
+    kind, st, pw, cone = PARTICLES[pname]
+    c.update(bc=[bc_pair[0], bc_pair[1], 2], kind=kind, sticking=st, power=pw, cone=cone)
+    run_pair(c, 40000)
