@@ -717,7 +717,7 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
     CK(cudaMemsetAsync(ctx->dCounterCopies, 0, VR_COUNTER_COPIES * 8 * sizeof(unsigned long long),
                        ctx->stream));
     CK(launchInitPool(p, ctx->stream));
-    CK(launchFlip(ctx->dSlotCursor, 0, ctx->stream));
+    CK(launchFlip(ctx->dSlotCursor, ctx->dCounterCopies, 0, ctx->stream));
     ctx->kernelLaunches += 2;
     // Wavefront iterations, launched in batches with one read-back (survivor
     // count, ray cursor) per batch.  While the source still has rays every slot
@@ -745,13 +745,13 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
         mark(ctx, 0);
         CK(launchShade(p, ctx->stream));
         mark(ctx, 1);
+        CK(launchFlip(ctx->dSlotCursor, ctx->dCounterCopies, p.compact, ctx->stream));
         if (b == batch - 1) {
-          CK(cudaMemcpyAsync(&ctx->hLive[0], p.liveCount, sizeof(unsigned int),
+          CK(cudaMemcpyAsync(&ctx->hLive[0], ctx->dSlotCursor + 3, sizeof(unsigned int),
                              cudaMemcpyDeviceToHost, ctx->stream));
           CK(cudaMemcpyAsync(&ctx->hLive[2], ctx->dCursor, sizeof(unsigned long long),
                              cudaMemcpyDeviceToHost, ctx->stream));
         }
-        CK(launchFlip(ctx->dSlotCursor, p.compact, ctx->stream));
         ctx->kernelLaunches += 3;
         ++ctx->iterations;
         if (compact) {

@@ -12,7 +12,7 @@
 #endif
 #define VR_LEAF_FLAG 0x80000000u  // child reference: leaf(first << 4 | count)
 #define VR_FIXED_SCALE 1073741824.0f
-#define VR_COUNTER_COPIES 16      // replicated TraceInfo counters (summed on download)
+#define VR_COUNTER_COPIES 64      // replicated TraceInfo counters (summed on download)
 
 namespace vr {
 
@@ -141,7 +141,8 @@ cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s);
 cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s);
 cudaError_t launchShade(const TraceParams &p, cudaStream_t s);
 // between iterations: resets the cursors; compact mode: slotCount = liveCount
-cudaError_t launchFlip(unsigned int *ctrl, int compact, cudaStream_t s);
+cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int compact,
+                       cudaStream_t s);
 cudaError_t launchDebugLoadRays(const DeviceScene &sc, const RayPool &pool, const float *rays,
                                 uint32_t m, cudaStream_t s);
 cudaError_t launchDebugReadHits(const DeviceScene &sc, const RayPool &pool, uint32_t m,

@@ -84,7 +84,8 @@ __device__ __forceinline__ void storeBoundaryHit(const DeviceScene &sc, const Ra
   best.t = 3.402823466e+38f;
   best.geom = best.prim = best.orig = VR_INVALID_ID;
   boundaryTest(sc, org, dir, best);
-  pool.hit[s] = make_float4(best.t, __uint_as_float(best.prim), __uint_as_float(best.geom), 0.f);
+  __stcs(&pool.hit[s],
+         make_float4(best.t, __uint_as_float(best.prim), __uint_as_float(best.geom), 0.f));
 }
 
 // Sky test: may the ray leaving `org` towards the source be declared free of
@@ -397,14 +398,15 @@ __device__ __forceinline__ void storeRay(const RayPool &pool, uint32_t s, const 
                                          const V3 &dir, const V3 &rayDirection, float w,
                                          const Rng &rng, uint64_t idx, uint32_t numReflections,
                                          uint32_t boundaryHits, bool hitFromBack) {
-  pool.od0[s] = make_float4(org.x, org.y, org.z, dir.x);
-  pool.od1[s] = make_float2(dir.y, dir.z);
-  pool.rng[s] = rng.save();
-  pool.meta[s] = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
-                            boundaryHits | (hitFromBack ? 0x80000000u : 0u));
-  pool.weight[s] = w;
+  // the pool is streamed (evict-first) so that the scene keeps the L2
+  __stcs(&pool.od0[s], make_float4(org.x, org.y, org.z, dir.x));
+  __stcs(&pool.od1[s], make_float2(dir.y, dir.z));
+  __stcs(&pool.rng[s], rng.save());
+  __stcs(&pool.meta[s], make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
+                                   boundaryHits | (hitFromBack ? 0x80000000u : 0u)));
+  __stcs(&pool.weight[s], w);
   if (D == 2)
-    pool.dir3[s] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f);
+    __stcs(&pool.dir3[s], make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f));
 }
 
 // ---------------------------------------------------------------------------
@@ -423,7 +425,6 @@ template <int D> __global__ void __launch_bounds__(256) initPoolKernel(const Tra
   if (ok) {
     storeRay<D>(p.pool, s, org, dir, rd, 1.f, rng, idx, 0u, 0u, false);
     storeBoundaryHit(p.scene, p.pool, s, org, dir);
-    atomicAdd(p.liveCount, 1u);
   } else {
     p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
   }
@@ -448,10 +449,6 @@ template <int D, int GEO>
 __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  __shared__ unsigned int shCount[12];
-  if (threadIdx.x < 12)
-    shCount[threadIdx.x] = 0u;
-  __syncthreads();
   const uint32_t numSlots = *p.slotCount;
 
   unsigned cTraces = 0, cMiss = 0, cGeo = 0, cBnd = 0, cRefl = 0, cTerm = 0, wNb = 0, wFlux = 0;
@@ -459,7 +456,7 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
   bool live = false, finish = false;
   float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
   if (s < numSlots)
-    a = p.pool.od0[s];
+    a = __ldcs(&p.pool.od0[s]);
   live = !slotEmpty(a);
 
   V3 org = {a.x, a.y, a.z}, dir = {0.f, 0.f, 0.f}, rayDirection = {0.f, 0.f, 0.f};
@@ -472,12 +469,13 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
   bh.geom = bh.prim = bh.orig = VR_INVALID_ID;
   Rng rng;
   rng.init(0, 0, 0);
+  uint4 rs = make_uint4(0u, 0u, 0u, 0u);
 
   if (live) {
-    const float2 b = p.pool.od1[s];
+    const float2 b = __ldcs(&p.pool.od1[s]);
     dir = {a.w, b.x, b.y};
     if (D == 2) {
-      const float4 r = p.pool.dir3[s];
+      const float4 r = __ldcs(&p.pool.dir3[s]);
       rayDirection = {r.x, r.y, r.z};
     } else {
       rayDirection = dir;
@@ -485,12 +483,13 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
     const float4 hv = __ldcs(&p.pool.hit[s]);
     const float ht = hv.x;
     const uint32_t hprim = __float_as_uint(hv.y), hgeom = __float_as_uint(hv.z);
-    const uint4 meta = p.pool.meta[s];
+    const uint4 meta = __ldcs(&p.pool.meta[s]);
     idx = (uint64_t)meta.x | ((uint64_t)meta.y << 32);
     numReflections = meta.z;
     boundaryHits = meta.w & 0x7fffffffu;
     hitFromBack = (meta.w >> 31) != 0u;
-    w = p.pool.weight[s];
+    w = __ldcs(&p.pool.weight[s]);
+    rs = __ldcs(&p.pool.rng[s]);  // issued with the other pool loads, not after the neighbour gathers
 
     ++cTraces;
     if (hgeom == VR_INVALID_ID) {  // :172
@@ -546,7 +545,7 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
               }
           }
         }
-        rng.load(p.pool.rng[s], p.seed, p.stream, idx);
+        rng.load(rs, p.seed, p.stream, idx);
         rngLoaded = true;
         const V3 newDir = surfaceReflection<D>(p.particle, rayDirection, gn, rng);  // :310
         w -= w * p.particle.sticking;                                               // :316
@@ -603,7 +602,7 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
           }
         }
         if (!finish)
-          p.pool.rng[s] = rng.save();
+          __stcs(&p.pool.rng[s], rng.save());
       }
     }
     if (finish) {
@@ -619,13 +618,14 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
   if (!p.compact) {
     if (live) {
       if (!finish) {
-        p.pool.od0[s] = make_float4(org.x, org.y, org.z, dir.x);
-        p.pool.od1[s] = make_float2(dir.y, dir.z);
-        p.pool.meta[s] = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
-                                    boundaryHits | (hitFromBack ? 0x80000000u : 0u));
-        p.pool.weight[s] = w;
+        __stcs(&p.pool.od0[s], make_float4(org.x, org.y, org.z, dir.x));
+        __stcs(&p.pool.od1[s], make_float2(dir.y, dir.z));
+        __stcs(&p.pool.meta[s], make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
+                                           boundaryHits | (hitFromBack ? 0x80000000u : 0u)));
+        __stcs(&p.pool.weight[s], w);
         if (D == 2)
-          p.pool.dir3[s] = make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f);
+          __stcs(&p.pool.dir3[s],
+                 make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f));
       } else if (regen) {
         storeRay<D>(p.pool, s, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
       } else {
@@ -633,7 +633,8 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
       }
       if (survive) {
         if (!finish && bhValid)  // the boundary hit of this ray is known already
-          p.pool.hit[s] = make_float4(bh.t, __uint_as_float(bh.prim), __uint_as_float(bh.geom), 0.f);
+          __stcs(&p.pool.hit[s], make_float4(bh.t, __uint_as_float(bh.prim),
+                                             __uint_as_float(bh.geom), 0.f));
         else
           storeBoundaryHit(sc, p.pool, s, org, dir);
       }
@@ -651,15 +652,15 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
         const uint32_t dst = base + __popc(m & ((1u << ln) - 1u));
         if (!finish) {
           if (!rngLoaded)
-            rng.load(p.pool.rng[s], p.seed, p.stream, idx);
+            rng.load(rs, p.seed, p.stream, idx);
           storeRay<D>(p.poolOut, dst, org, dir, rayDirection, w, rng, idx, numReflections,
                       boundaryHits, hitFromBack);
         } else {
           storeRay<D>(p.poolOut, dst, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
         }
         if (!finish && bhValid)
-          p.poolOut.hit[dst] =
-              make_float4(bh.t, __uint_as_float(bh.prim), __uint_as_float(bh.geom), 0.f);
+          __stcs(&p.poolOut.hit[dst], make_float4(bh.t, __uint_as_float(bh.prim),
+                                                  __uint_as_float(bh.geom), 0.f));
         else
           storeBoundaryHit(sc, p.poolOut, dst, org, dir);
       }
@@ -667,45 +668,57 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
   }
   const bool stillLive = survive && !p.compact;  // compact mode counted them above
 
-  // ---- counters: warp (REDUX) -> block -> one global atomic per block and counter ----
+  // ---- counters: warp sums (REDUX), then one global atomic per warp and counter on one
+  // of VR_COUNTER_COPIES replicas -- no block barrier, so a block's warps retire
+  // independently.  Replica word 0 carries the live count of the in-place mode.
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned vals[10] = {cTraces, cMiss, cGeo,  cBnd,  cRefl,
-                             cTerm,   stillLive ? 1u : 0u, wNb, wFlux, wSky};
+  unsigned long long *cnt =
+      p.counters + (size_t)((blockIdx.x * 8u + (threadIdx.x >> 5)) % VR_COUNTER_COPIES) * 8;
+  // TraceInfo words: 1 traces, 2 misses, 3 geometry hits, 5 boundary hits, 6 reflections,
+  // 7 terminated
+  const unsigned vals[7] = {stillLive ? 1u : 0u, cTraces, cMiss, cGeo, cBnd, cRefl, cTerm};
+  const int wordOf[7] = {0, 1, 2, 3, 5, 6, 7};
 #pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    if (k >= 7 && !p.work)
-      continue;
+  for (int k = 0; k < 7; ++k) {
     const unsigned v = __reduce_add_sync(0xffffffffu, vals[k]);
     if (lane == 0 && v)
-      atomicAdd(&shCount[k], v);
+      atomicAdd(&cnt[wordOf[k]], (unsigned long long)v);
   }
-  __syncthreads();
-  if (threadIdx.x < 10) {
-    const unsigned v = shCount[threadIdx.x];
-    if (v) {
-      unsigned long long *cnt = p.counters + (size_t)(blockIdx.x % VR_COUNTER_COPIES) * 8;
-      // TraceInfo slots: 1 traces, 2 misses, 3 geometry hits, 5 boundary hits,
-      // 6 reflections, 7 terminated
-      const int slotOf[6] = {1, 2, 3, 5, 6, 7};
-      if (threadIdx.x < 6)
-        atomicAdd(&cnt[slotOf[threadIdx.x]], (unsigned long long)v);
-      else if (threadIdx.x == 6)
-        atomicAdd(p.liveCount, v);
-      else if (p.work)
-        atomicAdd(&p.work[threadIdx.x - 5], (unsigned long long)v);  // 2 nb, 3 flux, 4 sky
+  if (p.work) {
+    const unsigned wv[3] = {wNb, wFlux, wSky};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned v = __reduce_add_sync(0xffffffffu, wv[k]);
+      if (lane == 0 && v)
+        atomicAdd(&p.work[2 + k], (unsigned long long)v);
     }
   }
 }
 
-// ctrl[0] slot cursor, ctrl[1] live count, ctrl[2] slots in use
-__global__ void flipKernel(unsigned int *ctrl, int compact) {
-  ctrl[0] = 0u;
-  if (compact)
-    ctrl[2] = ctrl[1];
-  ctrl[1] = 0u;
+// ctrl[0] slot cursor, ctrl[1] append cursor of the compacting mode, ctrl[2] slots in
+// use, ctrl[3] rays alive after the iteration (read back by the host).  In-place mode:
+// the live count is the sum of word 0 of the counter replicas (cleared here).
+__global__ void flipKernel(unsigned int *ctrl, unsigned long long *counters, int compact) {
+  unsigned long long v = 0;
+  for (int c = threadIdx.x; c < VR_COUNTER_COPIES; c += 32) {
+    v += counters[(size_t)c * 8];
+    counters[(size_t)c * 8] = 0ull;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_down_sync(0xffffffffu, v, o);
+  if (threadIdx.x == 0) {
+    const unsigned int live = compact ? ctrl[1] : (unsigned int)v;
+    ctrl[3] = live;
+    ctrl[0] = 0u;
+    if (compact)
+      ctrl[2] = live;
+    ctrl[1] = 0u;
+  }
 }
-cudaError_t launchFlip(unsigned int *ctrl, int compact, cudaStream_t s) {
-  flipKernel<<<1, 1, 0, s>>>(ctrl, compact);
+cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int compact,
+                       cudaStream_t s) {
+  flipKernel<<<1, 32, 0, s>>>(ctrl, counters, compact);
   return cudaGetLastError();
 }
 
