@@ -94,7 +94,13 @@ typedef struct {
   float posNeg;
   int32_t useBasis;
   float basis[9];
+  /* != 0: SourceGrid (raySourceGrid.hpp:9-74) over the origins given to
+   * vr_source_set_grid; ray idx starts at origin idx % numPoints */
+  int32_t useGrid;
 } vr_source_desc;
+
+/* origins (n x 3) of the grid source; copied to the device.  n == 0 releases them. */
+int vr_source_set_grid(vr_ctx *ctx, const float *points, uint32_t n);
 
 typedef struct {
   int32_t kind;       /* VR_PARTICLE_*                                       */

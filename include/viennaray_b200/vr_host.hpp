@@ -380,8 +380,60 @@ public:
                                                                   RNG &rngState) const = 0;
   [[nodiscard]] virtual std::size_t getNumPoints() const = 0;
   virtual NumericType getSourceArea() const = 0;
-  /// B200 path: device description of the source; false = host-only source.
-  virtual bool deviceSource(vr_source_desc &) const { return false; }
+  /// B200 path: device description of the source (and, for a grid source, its
+  /// origins as n x 3 floats); false = host-only source.
+  virtual bool deviceSource(vr_source_desc &, std::vector<float> &) const { return false; }
+};
+
+/// Rays start on a regular grid of origins, ray idx at origin idx % numPoints, with a
+/// cos^n direction distribution -- raySourceGrid.hpp:9-74.
+template <typename NumericType, int D> class SourceGrid : public Source<NumericType> {
+  using boundingBoxType = std::array<Vec3D<NumericType>, 2>;
+  const boundingBoxType bdBox_;
+  const std::vector<Vec3D<NumericType>> &sourceGrid_;
+  const std::array<int, 5> settings_;
+  const NumericType cosinePower_;
+
+public:
+  SourceGrid(const boundingBoxType &boundingBox, std::vector<Vec3D<NumericType>> &sourceGrid,
+             NumericType cosinePower, const std::array<int, 5> &traceSettings)
+      : bdBox_(boundingBox), sourceGrid_(sourceGrid), settings_(traceSettings),
+        cosinePower_(cosinePower) {}
+  std::array<Vec3D<NumericType>, 2> getOriginAndDirection(std::size_t idx, RNG &rngState) const override {
+    std::uniform_real_distribution<NumericType> uni;
+    const NumericType r1 = uni(rngState), r2 = uni(rngState);
+    const NumericType tt = std::pow(r2, NumericType(2) / (cosinePower_ + 1));
+    Vec3D<NumericType> d{0, 0, 0};
+    d[settings_[0]] = settings_[4] * std::sqrt(tt);
+    d[settings_[1]] = std::cos(NumericType(2 * M_PI) * r1) * std::sqrt(1 - tt);
+    d[settings_[2]] = D == 2 ? NumericType(0) : std::sin(NumericType(2 * M_PI) * r1) * std::sqrt(1 - tt);
+    Normalize(d);
+    return {sourceGrid_[idx % sourceGrid_.size()], d};
+  }
+  [[nodiscard]] std::size_t getNumPoints() const override { return sourceGrid_.size(); }
+  NumericType getSourceArea() const override {
+    const NumericType a = bdBox_[1][settings_[1]] - bdBox_[0][settings_[1]];
+    return D == 2 ? a : a * (bdBox_[1][settings_[2]] - bdBox_[0][settings_[2]]);
+  }
+  [[nodiscard]] NumericType getCosinePower() const { return cosinePower_; }
+  bool deviceSource(vr_source_desc &d, std::vector<float> &origins) const override {
+    for (int a = 0; a < 3; ++a) {
+      d.bboxMin[a] = static_cast<float>(bdBox_[0][a]);
+      d.bboxMax[a] = static_cast<float>(bdBox_[1][a]);
+    }
+    d.rayDir = settings_[0];
+    d.firstDir = settings_[1];
+    d.secondDir = settings_[2];
+    d.minMax = settings_[3];
+    d.posNeg = static_cast<float>(settings_[4]);
+    d.useBasis = 0;
+    d.useGrid = 1;
+    origins.resize(3 * sourceGrid_.size());
+    for (std::size_t i = 0; i < sourceGrid_.size(); ++i)
+      for (int a = 0; a < 3; ++a)
+        origins[3 * i + a] = static_cast<float>(sourceGrid_[i][a]);
+    return !origins.empty();
+  }
 };
 
 // ---- meshes (rayMesh.hpp:88-145), plain data ---------------------------------
@@ -451,6 +503,36 @@ void adjustBoundingBox(std::array<std::array<float, 3>, 2> &bbox, TraceDirection
     bbox[1][st[0]] += 2 * offset;
   else
     bbox[0][st[0]] -= 2 * offset;
+}
+
+// regular grid of about numPoints origins on the source plane, 1e-4 inside the lateral
+// box -- rayUtil.hpp:566-611
+template <class NumericType, int D>
+std::vector<Vec3D<NumericType>> createSourceGrid(const std::array<Vec3D<NumericType>, 2> &bdBox,
+                                                 const std::size_t numPoints, const NumericType gridDelta,
+                                                 const std::array<int, 5> &traceSettings) {
+  std::vector<Vec3D<NumericType>> grid;
+  const double eps = 1e-4;
+  const int rayDir = traceSettings[0], first = traceSettings[1], second = traceSettings[2],
+            minMax = traceSettings[3];
+  const auto len1 = bdBox[1][first] - bdBox[0][first], len2 = bdBox[1][second] - bdBox[0][second];
+  auto n1 = static_cast<std::size_t>(std::round(len1 / gridDelta));
+  auto n2 = static_cast<std::size_t>(std::round(len2 / gridDelta));
+  const unsigned long ratio = n1 / n2;
+  n1 = static_cast<std::size_t>(std::sqrt(numPoints * ratio));
+  n2 = static_cast<std::size_t>(std::sqrt(numPoints / ratio));
+  const auto d1 = (len1 - 2 * eps) / static_cast<NumericType>(n1 - 1);
+  const auto d2 = (len2 - 2 * eps) / static_cast<NumericType>(n2 - 1);
+  Vec3D<NumericType> point{};
+  point[rayDir] = bdBox[minMax][rayDir];
+  for (auto uu = bdBox[0][second] + eps; uu <= bdBox[1][second] - eps; uu += d2) {
+    point[second] = D == 2 ? NumericType(0) : static_cast<NumericType>(uu);
+    for (auto vv = bdBox[0][first] + eps; vv <= bdBox[1][first] - eps; vv += d1) {
+      point[first] = static_cast<NumericType>(vv);
+      grid.push_back(point);
+    }
+  }
+  return grid;
 }
 
 // rows u, v, w of the orthonormal basis whose first vector is `vec` -- rayUtil.hpp:287-321
@@ -668,12 +750,18 @@ protected:
       lastCond_[1] = condSecond;
     }
     vr_source_desc src{};
+    std::size_t sourcePoints = numPoints;  // SourceRandom: one "point" per primitive
     if (useCustomSource) {
-      if (!pSource_ || !pSource_->deviceSource(src)) {
+      std::vector<float> origins;
+      if (!pSource_ || !pSource_->deviceSource(src, origins) ||
+          (src.useGrid && vr_source_set_grid(ctx_, origins.data(),
+                                             static_cast<std::uint32_t>(origins.size() / 3)) != VR_OK)) {
         RTInfo_.error = true;
-        VIENNACORE_LOG_ERROR("Custom sources are host code and cannot be traced on the GPU. Aborting.");
+        VIENNACORE_LOG_ERROR("This custom source is host code and cannot be traced on the GPU "
+                             "(only SourceGrid has a device form). Aborting.");
         return false;
       }
+      sourcePoints = pSource_->getNumPoints();
     } else {
       for (int a = 0; a < 3; ++a) {
         src.bboxMin[a] = bbox[0][a];
@@ -697,7 +785,7 @@ protected:
     sourceArea_ = bbox[1][st[1]] - bbox[0][st[1]];
     if (D == 3)
       sourceArea_ *= bbox[1][st[2]] - bbox[0][st[2]];
-    sourcePoints_ = numPoints;
+    sourcePoints_ = sourcePoints;
 
     const auto labels = pParticle_->getLocalDataLabels();
     if (!labels.empty()) {
@@ -707,7 +795,7 @@ protected:
     }
 
     vr_config cfg{};
-    cfg.numRays = config_.numRaysFixed == 0 ? numPoints * config_.numRaysPerPoint : config_.numRaysFixed;
+    cfg.numRays = config_.numRaysFixed == 0 ? sourcePoints * config_.numRaysPerPoint : config_.numRaysFixed;
     cfg.rayIdxBegin = std::min<std::uint64_t>(shardBegin_, cfg.numRays);
     cfg.rayIdxEnd = std::min<std::uint64_t>(shardEnd_, cfg.numRays);
     // rayTraceKernel.hpp:100-104

@@ -75,6 +75,7 @@ def oracle_lib():
         L.vro_scene_set_disks.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_float]
         L.vro_scene_set_triangles.argtypes = [_vp, _vp, C.c_uint32, _vp, C.c_uint32]
         L.vro_scene_setup.argtypes = [_vp, C.c_int, _vp, C.c_float]
+        L.vro_scene_set_source_grid.argtypes = [_vp, _vp, C.c_uint32]
         L.vro_scene_bbox.argtypes = [_vp, _vp]
         L.vro_scene_num_prims.restype = C.c_uint32
         L.vro_scene_num_prims.argtypes = [_vp]
@@ -164,6 +165,14 @@ class OracleScene:
         rc = self.L.vro_scene_setup(self.h, source_dir, bc, np.float32(source_offset))
         if rc:
             raise ValueError("invalid trace set-up")
+
+    def set_source_grid(self, points):
+        """Grid source (raySourceGrid.hpp); None / empty returns to the random source."""
+        if points is None or len(points) == 0:
+            self.L.vro_scene_set_source_grid(self.h, None, 0)
+            return
+        points = np.ascontiguousarray(points, np.float32)
+        self.L.vro_scene_set_source_grid(self.h, _p(points), len(points))
 
     def bbox(self):
         out = np.zeros(6, np.float32)

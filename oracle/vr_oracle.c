@@ -227,6 +227,9 @@ struct vro_scene {
   int bc[2];
   float bverts[8][3];
   uint32_t btris[8][3];
+  /* optional grid source (raySourceGrid.hpp): origins, n x 3 */
+  float *grid;
+  uint32_t gridN;
   /* BVH over geometry primitives */
   node_t *nodes;
   uint32_t nNodes;
@@ -249,7 +252,21 @@ void vro_scene_destroy(vro_scene *s) {
   free(s->nbIdx);
   free(s->nodes);
   free(s->primOrder);
+  free(s->grid);
   free(s);
+}
+
+/* origins of a grid source (raySourceGrid.hpp); n == 0 returns to the random source */
+int vro_scene_set_source_grid(vro_scene *s, const float *points, uint32_t n) {
+  free(s->grid);
+  s->grid = NULL;
+  s->gridN = 0;
+  if (n) {
+    s->grid = (float *)malloc(sizeof(float) * 3 * (size_t)n);
+    memcpy(s->grid, points, sizeof(float) * 3 * (size_t)n);
+    s->gridN = n;
+  }
+  return 0;
 }
 uint32_t vro_scene_num_prims(const vro_scene *s) { return s->n; }
 void vro_scene_bbox(const vro_scene *s, float *o) {
@@ -927,7 +944,7 @@ int vro_boundary_process_hit(const vro_scene *s, float *org, float *rayDir3, flo
 
 /* raySourceRandom.hpp:50-116, rayUtil.hpp:287-321 */
 typedef struct {
-  float ee;
+  float ee, eeGrid;
   int custom;
   float B[3][3];
 } source_t;
@@ -936,6 +953,7 @@ static void source_init(const vro_scene *s, const vro_particle *p, const vro_con
                         source_t *src) {
   (void)s;
   src->ee = 1.0f / (p->sourcePower + 1.0f);
+  src->eeGrid = 2.0f / (p->sourcePower + 1.0f); /* raySourceGrid.hpp:21 */
   src->custom = c->usePrimaryDir;
   if (src->custom) {
     float u[3] = {c->primaryDir[0], c->primaryDir[1], c->primaryDir[2]};
@@ -959,8 +977,30 @@ static void source_init(const vro_scene *s, const vro_particle *p, const vro_con
   }
 }
 
-static void source_sample(const vro_scene *s, const source_t *src, rng_t *rng, float *origin,
-                          float *direction) {
+/* SourceGrid::getOriginAndDirection, raySourceGrid.hpp:23-52 */
+static void source_sample_grid(const vro_scene *s, const source_t *src, uint64_t idx, rng_t *rng,
+                               float *origin, float *direction) {
+  const float *g = s->grid + 3 * (size_t)(idx % s->gridN);
+  origin[0] = g[0];
+  origin[1] = g[1];
+  origin[2] = g[2];
+  float r1 = rng_f(rng), r2 = rng_f(rng);
+  float tt = pow_(r2, src->eeGrid);
+  float sinPhi, cosPhi;
+  sincos2pi(r1, &sinPhi, &cosPhi);
+  float st = sqrtf(1.f - tt);
+  direction[s->rayDir] = s->posNeg * sqrtf(tt);
+  direction[s->firstDir] = cosPhi * st;
+  direction[s->secondDir] = s->D == 2 ? 0.f : sinPhi * st;
+  normalize3(direction);
+}
+
+static void source_sample(const vro_scene *s, const source_t *src, uint64_t idx, rng_t *rng,
+                          float *origin, float *direction) {
+  if (s->gridN) {
+    source_sample_grid(s, src, idx, rng, origin, direction);
+    return;
+  }
   origin[0] = origin[1] = origin[2] = 0.f;
   float r1 = rng_f(rng);
   origin[s->rayDir] = s->bbox[s->minMax][s->rayDir];
@@ -1004,7 +1044,7 @@ static void trace_one(const vro_scene *s, const vro_particle *p, const vro_confi
   const float initialWeight = 1.f; /* raySource.hpp:18 */
   float w = initialWeight;
   float org[3], rayDirection[3], dir[3];
-  source_sample(s, src, &rng, org, rayDirection);
+  source_sample(s, src, idx, &rng, org, rayDirection);
   fill_dir(s->D, rayDirection, dir);
   unsigned numReflections = 0, boundaryHits = 0;
   int hitFromBack = 0;
@@ -1124,7 +1164,7 @@ int vro_source_rays(const vro_scene *s, const vro_particle *p, const vro_config 
     rng_t rng;
     rng_init(&rng, c->seed, c->stream, idxBegin + i);
     float d[3];
-    source_sample(s, &src, &rng, rays + 6 * i, d);
+    source_sample(s, &src, idxBegin + i, &rng, rays + 6 * i, d);
     fill_dir(s->D, d, rays + 6 * i + 3);
   }
   return 0;

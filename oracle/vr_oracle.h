@@ -67,6 +67,8 @@ int vro_scene_set_triangles(vro_scene *s, const float *verts, uint32_t nVerts,
 /* sourceOffset: disk radius (rayTraceDisk.hpp:21-23) or gridDelta
  * (rayTraceTriangle.hpp:21-23) */
 int vro_scene_setup(vro_scene *s, int sourceDir, const int *bc, float sourceOffset);
+/* SourceGrid (raySourceGrid.hpp:9-74): origins points[idx % n]; n == 0: random source */
+int vro_scene_set_source_grid(vro_scene *s, const float *points, uint32_t n);
 void vro_scene_bbox(const vro_scene *s, float *out6);
 uint32_t vro_scene_num_prims(const vro_scene *s);
 void vro_scene_neighbors(const vro_scene *s, const uint32_t **offsets, const uint32_t **indices);

@@ -277,6 +277,50 @@ static void testTraceInterface(const std::string &out) {
   VC_TEST_ASSERT(userTracer.getRayTraceInfo().error);
 }
 
+// tests/createSourceGrid/createSourceGrid.cpp:43-46 and a trace through setSource()
+static void testSourceGrid(const std::string &out) {
+  std::vector<Vec3D<float>> points, normals;
+  planeGrid<float>(0.5f, 5.f, {0, 1, 2}, points, normals);
+  TraceDisk<float, 3> tracer;
+  tracer.setGeometry(points, normals, 0.5f);
+  auto bb = tracer.getBoundingBox();
+  rayInternal::adjustBoundingBox<3>(bb, TraceDirection::POS_Z, float(0.5 * rayInternal::DiskFactor<3>));
+  std::array<Vec3D<float>, 2> bdBox = {Vec3D<float>{bb[0][0], bb[0][1], bb[0][2]},
+                                       Vec3D<float>{bb[1][0], bb[1][1], bb[1][2]}};
+  const auto settings = rayInternal::getTraceSettings(TraceDirection::POS_Z);
+  auto grid = rayInternal::createSourceGrid<float, 3>(bdBox, points.size(), 0.5f, settings);
+  VC_TEST_ASSERT(grid.size() > 100 && grid.size() <= points.size());
+  auto source = std::make_shared<SourceGrid<float, 3>>(bdBox, grid, 1.f, settings);
+  RNG rng(0);
+  for (std::size_t i = 0; i < grid.size(); ++i) {
+    auto od = source->getOriginAndDirection(i, rng);
+    VC_TEST_ASSERT(od[1][2] < 0.f);
+    VC_TEST_ASSERT_ISCLOSE(od[0][2], bb[1][2], 1e-6);
+    VC_TEST_ASSERT_ISCLOSE(od[0][0], grid[i][0], 1e-6);
+    VC_TEST_ASSERT_ISCLOSE(od[0][1], grid[i][1], 1e-6);
+  }
+  if (out.empty())
+    return;
+  auto particle = std::make_unique<DiffuseParticle<float, 3>>(1.0f, "flux");
+  tracer.setParticleType(particle);
+  tracer.setSource(source);
+  tracer.setNumberOfRaysPerPoint(20);
+  tracer.setRngSeed(5);
+  tracer.apply();
+  auto info = tracer.getRayTraceInfo();
+  VC_TEST_ASSERT(!info.error);
+  VC_TEST_ASSERT(info.numRays == 20 * grid.size());
+  auto flux = tracer.getLocalData().getVectorData(0);
+  double sum = 0;
+  for (auto f : flux)
+    sum += f;
+  VC_TEST_ASSERT(sum >= double(info.numRays)); // every ray lands on the plane at least once
+  tracer.resetSource();
+  tracer.apply();
+  VC_TEST_ASSERT(tracer.getRayTraceInfo().numRays == 20 * points.size());
+  dump(out + "/sourceGrid_flux.f32", flux);
+}
+
 // examples/triangle3D-style run on a two-triangle floor + tests/trace2D
 static void testTriangleAnd2D(const std::string &out) {
   {
@@ -354,11 +398,14 @@ int main(int argc, char **argv) {
   testNeighborsAndAreas();
   testBoundingBox();
   testNoFallback();
+  if (mode != "gpu")
+    testSourceGrid("");
   if (mode == "gpu") {
     const std::string out = argc > 2 ? argv[2] : ".";
     testRngSeed(out);
     testTraceInterface(out);
     testTriangleAnd2D(out);
+    testSourceGrid(out);
   }
   if (failures) {
     std::fprintf(stderr, "%d assertion(s) failed\n", failures);

@@ -250,3 +250,39 @@ def test_neighbor_build_on_device(name):
     fo, _ = orc.trace(common.oracle_particle(c), orc.config(60000, SEED))
     assert (ctx.flux_download_fixed()[0] == fo).all()
     ctx.close()
+
+
+@pytest.mark.parametrize("name,power", [("trench", 1.0), ("trench_ion", 100.0), ("disk2D", 1.0),
+                                        ("triangle3D", 3.0)])
+def test_grid_source(name, power):
+    """SourceGrid (SURVEY 8f-3, raySourceGrid.hpp): origins idx % numPoints, cos^n direction;
+    source rays and whole walks bit-equal to the oracle."""
+    c = common.case(name)
+    c["power"] = power
+    orc = common.make_oracle(c)
+    ctx, _, st = common.make_gpu(c)
+    lo, hi = st["bbox"]
+    if c["D"] == 3:  # 37 x 23 origins on the source plane
+        gx, gy = np.meshgrid(np.linspace(lo[0] + 1e-4, hi[0] - 1e-4, 37, dtype=np.float32),
+                             np.linspace(lo[1] + 1e-4, hi[1] - 1e-4, 23, dtype=np.float32))
+        grid = np.stack([gx.ravel(), gy.ravel(), np.full(gx.size, hi[2], np.float32)], 1)
+    else:
+        grid = np.stack([np.linspace(lo[0] + 1e-4, hi[0] - 1e-4, 50, dtype=np.float32),
+                         np.full(50, hi[1], np.float32), np.zeros(50, np.float32)], 1)
+    orc.set_source_grid(grid)
+    ctx.set_source_grid(grid)
+    src = host.source_desc(lo, hi, c["source_dir"], use_grid=True)
+    m = 30000
+    ro = orc.source_rays(common.oracle_particle(c), orc.config(10**6, SEED), 77, m)
+    rg = ctx.debug_source_rays(src, common.gpu_particle(c), host.config(10**6, SEED), 77, m)
+    assert (ro.view(np.uint32) == rg.view(np.uint32)).all()
+    num = 100000
+    fo, io = orc.trace(common.oracle_particle(c), orc.config(num, SEED))
+    ctx.trace_device(src, [common.gpu_particle(c)], host.config(num, SEED), sync=True)
+    assert (ctx.flux_download_fixed()[0] == fo).all()
+    assert ctx.flux_download()[1][0].totalRaysTraced == io.totalTraces
+    # a grid source without grid points is a state error, not a silent fallback
+    ctx.set_source_grid(None)
+    with pytest.raises(capi.VrError):
+        ctx.trace_device(src, [common.gpu_particle(c)], host.config(100, SEED), sync=True)
+    ctx.close()

@@ -305,3 +305,32 @@ def test_flux_statistical_parity_with_reference_kernel(name, rays_per_prim):
     tr_o, tr_r = io.totalTraces / num, ir[1] / num
     assert abs(tr_o - tr_r) / tr_r < 0.01
     assert abs(io.geoHits / num - ir[3] / num) / (ir[3] / num) < 0.01
+
+
+# --------------------------------------------------------------------------------------
+# tests/createSourceGrid/createSourceGrid.cpp:43-46
+# --------------------------------------------------------------------------------------
+def test_source_grid_origins_and_direction():
+    I = common.inputs()
+    gd = F(I["sphere3D_gridDelta"])
+    s = po.OracleScene(3)
+    s.set_disks(I["sphere3D_points"], I["sphere3D_normals"], gd)
+    s.setup(po.POS_Z, [0, 0, 0], gd)
+    lo, hi = s.bbox()
+    grid = host.create_source_grid(lo, hi, len(I["sphere3D_points"]), gd, host.POS_Z)
+    assert 100 < len(grid) <= len(I["sphere3D_points"])
+    s.set_source_grid(grid)
+    m = len(grid)
+    rays = s.source_rays(po.Particle(0, 1.0, 1.0, 0.0), s.config(m, 0), 0, 2 * m)
+    assert (rays[:, 5] < 0).all()
+    assert np.allclose(rays[:, 2], 1.0 + 2 * gd, atol=1e-6)
+    assert np.allclose(rays[:m, 0], grid[:, 0], atol=1e-6)
+    assert np.allclose(rays[:m, 1], grid[:, 1], atol=1e-6)
+    assert (rays[m:, :3] == rays[:m, :3]).all()  # idx % numPoints
+    assert np.allclose(np.linalg.norm(rays[:, 3:], axis=1), 1, atol=1e-5)
+    # cos^n source: E[cos theta] = 2/3 for n = 1 (raySourceGrid.hpp:42-51)
+    big = s.source_rays(po.Particle(0, 1.0, 1.0, 0.0), s.config(10**6, 5), 0, 200000)
+    assert abs((-big[:, 5]).mean() - 2.0 / 3.0) < 3e-3
+    s.set_source_grid(None)
+    back = s.source_rays(po.Particle(0, 1.0, 1.0, 0.0), s.config(m, 0), 0, 10)
+    assert not np.allclose(back[:, 0], grid[:10, 0])

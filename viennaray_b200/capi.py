@@ -18,7 +18,7 @@ BOUNDARY_REFLECTIVE, BOUNDARY_PERIODIC, BOUNDARY_IGNORE = 0, 1, 2
 EXPORTS = [
     "vr_ctx_create", "vr_ctx_destroy", "vr_last_error", "vr_scene_set_disks",
     "vr_scene_set_triangles", "vr_scene_build_neighbors", "vr_scene_get_neighbors",
-    "vr_scene_set_boundary", "vr_scene_commit", "vr_trace",
+    "vr_scene_set_boundary", "vr_source_set_grid", "vr_scene_commit", "vr_trace",
     "vr_trace_device", "vr_flux_device", "vr_flux_download", "vr_flux_download_fixed",
     "vr_flux_postprocess",
     "vr_ctx_stream", "vr_ctx_synchronize", "vr_last_kernel_ms", "vr_last_launch_count", "vr_build_neighbors", "vr_free",
@@ -31,7 +31,8 @@ EXPORTS = [
 class SourceDesc(C.Structure):
     _fields_ = [("bboxMin", C.c_float * 3), ("bboxMax", C.c_float * 3), ("rayDir", C.c_int32),
                 ("firstDir", C.c_int32), ("secondDir", C.c_int32), ("minMax", C.c_int32),
-                ("posNeg", C.c_float), ("useBasis", C.c_int32), ("basis", C.c_float * 9)]
+                ("posNeg", C.c_float), ("useBasis", C.c_int32), ("basis", C.c_float * 9),
+                ("useGrid", C.c_int32)]
 
 
 class ParticleDesc(C.Structure):
@@ -82,6 +83,7 @@ def lib():
         L.vr_scene_set_boundary.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int]
         L.vr_scene_commit.argtypes = [_vp]
+        L.vr_source_set_grid.argtypes = [_vp, _vp, C.c_uint32]
         L.vr_scene_build_neighbors.argtypes = [_vp, C.c_int, _vp, C.c_float]
         L.vr_scene_get_neighbors.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp)]
         L.vr_trace.argtypes = [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp]
@@ -208,6 +210,14 @@ class Context:
         hi = np.ascontiguousarray(bbox_max, np.float32)
         self._ck(self.L.vr_scene_set_boundary(self.h, _p(lo), _p(hi), first_dir, second_dir,
                                               cond_first, cond_second, D))
+
+    def set_source_grid(self, points):
+        """Origins of the grid source (raySourceGrid.hpp); None releases them."""
+        if points is None or len(points) == 0:
+            self._ck(self.L.vr_source_set_grid(self.h, None, 0))
+            return
+        points = np.ascontiguousarray(points, np.float32)
+        self._ck(self.L.vr_source_set_grid(self.h, _p(points), len(points)))
 
     def commit(self):
         self._ck(self.L.vr_scene_commit(self.h))

@@ -58,6 +58,8 @@ struct vr_ctx {
   int kernelLaunches = 0;
   int iterations = 0;
   bool countWork = false;
+  float *dGrid = nullptr;  // grid source origins
+  uint32_t gridN = 0;
   // sky map (escape culling), built lazily for the source axis / side of a trace
   float2 *dSky = nullptr;
   int skyAxis = -1;
@@ -288,6 +290,7 @@ void vr_ctx_destroy(vr_ctx *ctx) {
   if (ctx->stream) {
     freeDeviceScene(ctx);
     freeInputs(ctx);
+    cudaFreeAsync(ctx->dGrid, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
   }
   freeResults(ctx);
@@ -420,6 +423,23 @@ int vr_scene_set_triangles(vr_ctx *ctx, const float *verts, uint32_t nVerts, con
     ctx->materialIds.assign(materialIds, materialIds + n);
   else
     ctx->materialIds.assign(n, 0);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VR_OK;
+}
+
+int vr_source_set_grid(vr_ctx *ctx, const float *points, uint32_t n) {
+  if (!ctx)
+    return VR_ERR_ARGUMENT;
+  if (n && !points)
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_source_set_grid: null points");
+  CK(cudaSetDevice(ctx->device));
+  cudaFreeAsync(ctx->dGrid, ctx->stream);
+  ctx->dGrid = nullptr;
+  ctx->gridN = 0;
+  if (n) {
+    CK(uploadArray(ctx, &ctx->dGrid, points, (size_t)3 * n));
+    ctx->gridN = n;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   return VR_OK;
 }
@@ -622,6 +642,15 @@ static int fillParams(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_
   p.src = *src;
   p.particle = *part;
   p.ee = 1.0f / (part->sourcePower + 1.0f);
+  p.eeGrid = 2.0f / (part->sourcePower + 1.0f);
+  p.grid = nullptr;
+  p.gridN = 0;
+  if (src->useGrid) {
+    if (!ctx->dGrid || ctx->gridN == 0)
+      return fail(ctx, VR_ERR_STATE, "trace: grid source without vr_source_set_grid");
+    p.grid = ctx->dGrid;
+    p.gridN = ctx->gridN;
+  }
   p.idxBegin = cfg->rayIdxBegin;
   p.idxEnd = cfg->rayIdxEnd;
   p.seed = cfg->seed;

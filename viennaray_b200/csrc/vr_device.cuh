@@ -434,6 +434,24 @@ __device__ __forceinline__ V3 surfaceReflection(const vr_particle_desc &p, const
   return reflectConedCosine<D>(d, n, rng, 1.57079637050628662f - m);
 }
 
+// raySourceGrid.hpp:23-52
+template <int D>
+__device__ __forceinline__ void sourceSampleGrid(const vr_source_desc &s, const float *grid,
+                                                 uint32_t gridN, float eeGrid, uint64_t idx,
+                                                 Rng &rng, V3 &origin, V3 &direction) {
+  const float *g = grid + 3 * (size_t)(idx % gridN);
+  origin = {g[0], g[1], g[2]};
+  const float r1 = rng.f(), r2 = rng.f();
+  const float tt = powdet(r2, eeGrid);
+  float sinPhi, cosPhi;
+  sincos2pi(r1, sinPhi, cosPhi);
+  const float st = sqrtf(1.f - tt);
+  setComp(direction, s.rayDir, s.posNeg * sqrtf(tt));
+  setComp(direction, s.firstDir, cosPhi * st);
+  setComp(direction, s.secondDir, D == 2 ? 0.f : sinPhi * st);
+  normalize(direction);
+}
+
 // raySourceRandom.hpp:50-116
 template <int D>
 __device__ __forceinline__ void sourceSample(const vr_source_desc &s, float ee, Rng &rng,

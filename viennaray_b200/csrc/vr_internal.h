@@ -75,7 +75,10 @@ struct TraceParams {
   int compact;      // 0: survivors stay in place; 1: append to poolOut
   vr_source_desc src;
   vr_particle_desc particle;
-  float ee;  // 1 / (sourcePower + 1), raySourceRandom.hpp:21
+  float ee;      // 1 / (sourcePower + 1), raySourceRandom.hpp:21
+  float eeGrid;  // 2 / (sourcePower + 1), raySourceGrid.hpp:21
+  const float *grid;  // grid source origins (n x 3) or null
+  uint32_t gridN;
   uint64_t idxBegin, idxEnd;
   uint32_t seed, stream;
   uint32_t maxReflections, maxBoundaryHits;

@@ -388,7 +388,10 @@ __device__ __forceinline__ bool regenerate(const TraceParams &p, bool want, uint
     return false;
   idx = p.idxBegin + off;
   rng.init(p.seed, p.stream, idx);
-  sourceSample<D>(p.src, p.ee, rng, org, rayDirection);
+  if (p.grid)
+    sourceSampleGrid<D>(p.src, p.grid, p.gridN, p.eeGrid, idx, rng, org, rayDirection);
+  else
+    sourceSample<D>(p.src, p.ee, rng, org, rayDirection);
   dir = fillDir<D>(rayDirection);
   return true;
 }
@@ -862,8 +865,11 @@ __global__ void debugSourceKernel(TraceParams p, uint64_t idxBegin, uint32_t m, 
     return;
   Rng rng;
   rng.init(p.seed, p.stream, idxBegin + i);
-  V3 org, d;
-  sourceSample<D>(p.src, p.ee, rng, org, d);
+  V3 org, d = {0.f, 0.f, 0.f};
+  if (p.grid)
+    sourceSampleGrid<D>(p.src, p.grid, p.gridN, p.eeGrid, idxBegin + i, rng, org, d);
+  else
+    sourceSample<D>(p.src, p.ee, rng, org, d);
   V3 dir = fillDir<D>(d);
   rays[6 * i] = org.x;
   rays[6 * i + 1] = org.y;

@@ -67,8 +67,37 @@ def orthonormal_basis(vec):
     return np.stack([u, h, w]).astype(F)
 
 
-def source_desc(lo, hi, source_dir, primary_dir=None):
+def create_source_grid(lo, hi, num_points, grid_delta, source_dir, D=3):
+    """Origins of rayInternal::createSourceGrid (rayUtil.hpp:566-611): a regular grid of about
+    num_points points on the source plane, 1e-4 inside the lateral box."""
+    axis, first, second, min_max, _ = trace_settings(source_dir)
+    eps = 1e-4
+    len1, len2 = F(hi[first] - lo[first]), F(hi[second] - lo[second])
+    n1, n2 = int(round(float(len1 / F(grid_delta)))), int(round(float(len2 / F(grid_delta))))
+    ratio = n1 // n2
+    if ratio == 0:  # the reference divides by this integer ratio (rayUtil.hpp:584-586)
+        raise ValueError("createSourceGrid needs the first lateral extent >= the second")
+    n1, n2 = int(np.sqrt(num_points * ratio)), int(np.sqrt(num_points / ratio))
+    d1 = F((len1 - 2 * eps) / F(n1 - 1))
+    d2 = F((len2 - 2 * eps) / F(n2 - 1))
+    pts = []
+    uu = F(lo[second] + eps)
+    while uu <= hi[second] - eps:
+        vv = F(lo[first] + eps)
+        while vv <= hi[first] - eps:
+            p = [F(0)] * 3
+            p[axis] = F((hi if min_max else lo)[axis])
+            p[second] = F(0) if D == 2 else uu
+            p[first] = vv
+            pts.append(p)
+            vv = F(vv + d1)
+        uu = F(uu + d2)
+    return np.asarray(pts, F)
+
+
+def source_desc(lo, hi, source_dir, primary_dir=None, use_grid=False):
     s = capi.SourceDesc()
+    s.useGrid = 1 if use_grid else 0
     s.bboxMin[:] = [float(x) for x in lo]
     s.bboxMax[:] = [float(x) for x in hi]
     s.rayDir, s.firstDir, s.secondDir, s.minMax, pn = trace_settings(source_dir)
