@@ -107,6 +107,8 @@ typedef struct {
   float sticking;     /* constant sticking probability                       */
   float sourcePower;  /* getSourceDistributionPower()                        */
   float coneMinAngle; /* coned cosine: cone = pi/2 - min(incAngle, this)     */
+  float meanFreePath; /* getMeanFreePath(); <= 0: no scattering
+                         (rayTraceKernel.hpp:179-203)                       */
 } vr_particle_desc;
 
 /* KernelConfig (rayUtil.hpp:83-94) + the ray-index shard of this context */
@@ -117,8 +119,12 @@ typedef struct {
   uint32_t seed;         /* runNumber + rngSeed (rayTraceKernel.hpp:100)     */
   uint32_t maxReflections;
   uint32_t maxBoundaryHits;
-  uint32_t reserved;
+  uint32_t flags;        /* VR_FLAG_*                                        */
 } vr_config;
+
+/* distance-weighted neighbour spread, the reference's compile-time option
+ * VIENNARAY_USE_WDIST (rayTraceKernel.hpp:258-296) */
+#define VR_FLAG_WDIST 1u
 
 /* TraceInfo (rayUtil.hpp:65-76) plus rays cut by the hit limits */
 typedef struct {

@@ -728,11 +728,7 @@ protected:
                            "can be traced on the GPU. Aborting.");
       return false;
     }
-    if (pParticle_->getMeanFreePath() > 0) {
-      RTInfo_.error = true;
-      VIENNACORE_LOG_ERROR("Mean-free-path scattering is not available on the GPU path. Aborting.");
-      return false;
-    }
+    pd.meanFreePath = static_cast<float>(pParticle_->getMeanFreePath()); // <= 0: no scattering
     rayInternal::adjustBoundingBox<D>(bbox, sourceDirection_, sourceOffset);
     const auto st = rayInternal::getTraceSettings(sourceDirection_);
     const int condFirst = static_cast<int>(boundaryConditions_[st[1]]);
@@ -802,6 +798,9 @@ protected:
     cfg.seed = config_.useRandomSeed ? std::random_device{}() : config_.runNumber + config_.rngSeed;
     cfg.maxReflections = config_.maxReflections;
     cfg.maxBoundaryHits = config_.maxBoundaryHits;
+#ifdef VIENNARAY_USE_WDIST // the reference's compile-time option (CMakeLists.txt:70-73)
+    cfg.flags |= VR_FLAG_WDIST;
+#endif
     std::vector<double> flux(numPoints);
     vr_trace_info info{};
     if (vr_trace(ctx_, &src, &pd, 1, &cfg, flux.data(), &info) != VR_OK) {

@@ -36,13 +36,14 @@ def build(reference_root="/root/reference"):
 
 class Particle(C.Structure):
     _fields_ = [("kind", C.c_int), ("sticking", C.c_float), ("sourcePower", C.c_float),
-                ("coneMinAngle", C.c_float)]
+                ("coneMinAngle", C.c_float), ("meanFreePath", C.c_float)]
 
 
 class Config(C.Structure):
     _fields_ = [("numRays", C.c_uint64), ("seed", C.c_uint32), ("stream", C.c_uint32),
                 ("maxReflections", C.c_uint32), ("maxBoundaryHits", C.c_uint32),
-                ("usePrimaryDir", C.c_int), ("primaryDir", C.c_float * 3)]
+                ("usePrimaryDir", C.c_int), ("primaryDir", C.c_float * 3),
+                ("useWdist", C.c_int)]
 
 
 class Info(C.Structure):
@@ -195,9 +196,9 @@ class OracleScene:
 
     @staticmethod
     def config(num_rays, seed, stream=0, max_reflections=0xFFFFFFFF, max_boundary_hits=1000,
-               primary_dir=None):
+               primary_dir=None, wdist=False):
         c = Config(num_rays, seed, stream, max_reflections, max_boundary_hits,
-                   0 if primary_dir is None else 1, (C.c_float * 3)(0, 0, 0))
+                   0 if primary_dir is None else 1, (C.c_float * 3)(0, 0, 0), 1 if wdist else 0)
         if primary_dir is not None:
             c.primaryDir[:] = [float(x) for x in primary_dir]
         return c

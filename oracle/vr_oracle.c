@@ -763,8 +763,8 @@ static void intersect(const vro_scene *s, const float *org, const float *dir, hi
 }
 
 /* rayTraceKernel.hpp:462-507 checkLocalIntersection */
-static inline int check_local(const vro_scene *s, const float *org, const float *dir,
-                              uint32_t prim) {
+static inline int check_local_d(const vro_scene *s, const float *org, const float *dir,
+                                uint32_t prim, float *distOut) {
   const float *n = s->normal + 3 * prim, *c = s->disk + 4 * prim;
   float prod = dot3(n, dir);
   if (prod > 0.f)
@@ -779,7 +779,13 @@ static inline int check_local(const vro_scene *s, const float *org, const float 
   for (int i = 0; i < 3; ++i)
     hp[i] = (org[i] + dir[i] * tt) - c[i];
   float distance = sqrtf(dot3(hp, hp));
+  *distOut = distance;
   return c[3] > distance;
+}
+static inline int check_local(const vro_scene *s, const float *org, const float *dir,
+                              uint32_t prim) {
+  float d;
+  return check_local_d(s, org, dir, prim, &d);
 }
 
 /* rayUtil.hpp:204-215 fillRayDirection<D>: ray.dir from the particle-facing
@@ -1056,6 +1062,27 @@ static void trace_one(const vro_scene *s, const vro_particle *p, const vro_confi
       info->nonGeoHits++;
       break;
     }
+    if (p->meanFreePath > 0.f) { /* :179-203 scattering event */
+      float scatterProbability = 1.f - exp2_((-h.t / p->meanFreePath) * 1.4426950216293335f);
+      float rnd = rng_f(&rng);
+      if (rnd < scatterProbability) {
+        for (int i = 0; i < 3; ++i)
+          org[i] = org[i] + dir[i] * rnd; /* sic: moved by the uniform draw, :188-190 */
+        float x, y, s2; /* pickRandomPointOnUnitSphere, rayUtil.hpp:266-283 */
+        do {
+          x = 2.f * rng_f(&rng) - 1.f;
+          y = 2.f * rng_f(&rng) - 1.f;
+          s2 = x * x + y * y;
+        } while (s2 >= 1.f);
+        float tmp = 2.f * sqrtf(1.f - s2);
+        rayDirection[0] = x * tmp;
+        rayDirection[1] = y * tmp;
+        rayDirection[2] = 1.f - 2.f * s2;
+        fill_dir(s->D, rayDirection, dir);
+        info->particleHits++;
+        continue;
+      }
+    }
     if (h.geom == 0u) { /* :206-214 */
       if (++boundaryHits > c->maxBoundaryHits) {
         info->raysTerminated++;
@@ -1084,7 +1111,33 @@ static void trace_one(const vro_scene *s, const vro_particle *p, const vro_confi
     }
     info->geoHits++;
     uint64_t wf = to_fixed(w);
-    if (s->geoType == 0) { /* :255-300 */
+    if (s->geoType == 0 && c->useWdist) { /* :258-296 with VIENNARAY_USE_WDIST */
+      uint32_t ids[64];
+      float dist[64];
+      uint32_t nh = 1;
+      ids[0] = h.prim;
+      {
+        const float *dc = s->disk + 4 * h.prim;
+        float q[3] = {hitPoint[0] - dc[0], hitPoint[1] - dc[1], hitPoint[2] - dc[2]};
+        dist[0] = sqrtf(dot3(q, q)) + 1e-6f;
+      }
+      for (uint32_t k = s->nbOff[h.prim]; k < s->nbOff[h.prim + 1]; ++k) {
+        uint32_t id = s->nbIdx[k];
+        float d;
+        if (check_local_d(s, org, dir, id, &d) && nh < 64) {
+          ids[nh] = id;
+          dist[nh++] = d + 1e-6f;
+        }
+      }
+      float invSum = 0.f;
+      for (uint32_t k = 0; k < nh; ++k)
+        invSum += 1.f / dist[k];
+      for (uint32_t k = 0; k < nh; ++k) {
+        uint64_t wk = to_fixed(((w / dist[k]) / invSum) * (float)nh);
+#pragma omp atomic
+        flux[ids[k]] += wk;
+      }
+    } else if (s->geoType == 0) { /* :255-300 */
 #pragma omp atomic
       flux[h.prim] += wf;
       for (uint32_t k = s->nbOff[h.prim]; k < s->nbOff[h.prim + 1]; ++k) {
@@ -1141,6 +1194,7 @@ int vro_trace(const vro_scene *s, const vro_particle *p, const vro_config *c, ui
       total.totalTraces += local.totalTraces;
       total.nonGeoHits += local.nonGeoHits;
       total.geoHits += local.geoHits;
+      total.particleHits += local.particleHits;
       total.boundaryHits += local.boundaryHits;
       total.reflections += local.reflections;
       total.raysTerminated += local.raysTerminated;
@@ -1150,6 +1204,7 @@ int vro_trace(const vro_scene *s, const vro_particle *p, const vro_config *c, ui
   info->totalTraces += total.totalTraces;
   info->nonGeoHits += total.nonGeoHits;
   info->geoHits += total.geoHits;
+  info->particleHits += total.particleHits;
   info->boundaryHits += total.boundaryHits;
   info->reflections += total.reflections;
   info->raysTerminated += total.raysTerminated;

@@ -41,6 +41,7 @@ typedef struct {
   float sticking;     /* constant sticking probability */
   float sourcePower;  /* cosine exponent of the source (1 = cosine) */
   float coneMinAngle; /* coned cosine: cone = pi/2 - min(incAngle, this) */
+  float meanFreePath; /* getMeanFreePath(); <= 0: no scattering (rayTraceKernel.hpp:179) */
 } vro_particle;
 
 typedef struct {
@@ -51,6 +52,7 @@ typedef struct {
   uint32_t maxBoundaryHits;
   int usePrimaryDir;
   float primaryDir[3];
+  int useWdist; /* VIENNARAY_USE_WDIST: distance-weighted neighbour spread */
 } vro_config;
 
 typedef struct {

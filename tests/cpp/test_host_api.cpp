@@ -99,6 +99,17 @@ static void testParticle() {
   VC_TEST_ASSERT(ion->deviceParticle(d) && d.kind == VR_PARTICLE_CONED_COSINE);
 }
 
+// a built-in particle with a mean free path (AbstractParticle::getMeanFreePath)
+template <class T> class ScatteringParticle : public Particle<ScatteringParticle<T>, T> {
+public:
+  T getMeanFreePath() const override { return T(3); }
+  std::vector<std::string> getLocalDataLabels() const override { return {"flux"}; }
+  bool deviceParticle(vr_particle_desc &d) const override {
+    d = {VR_PARTICLE_DIFFUSE, 0.2f, 1.f, 0.f, 0.f};
+    return true;
+  }
+};
+
 // a user particle with host-side hooks: must be refused, never run on the CPU
 template <class T> class UserParticle : public Particle<UserParticle<T>, T> {
 public:
@@ -267,6 +278,19 @@ static void testTraceInterface(const std::string &out) {
   auto flux2 = rayTracer.getLocalData().getVectorData("hitFlux");
   VC_TEST_ASSERT(std::memcmp(flux2.data(), rayTracer.getLocalData().getVectorData(0).data(), 4 * 441) == 0);
   dump(out + "/traceInterface_run2.f32", flux2);
+
+  // mean-free-path scattering shows up in TraceInfo::particleHits (rayTraceKernel.hpp:179-203)
+  {
+    TraceDisk<float, 3> mfpTracer;
+    auto sp = std::make_unique<ScatteringParticle<float>>();
+    mfpTracer.setParticleType(sp);
+    mfpTracer.setGeometry(points, normals, 0.5f);
+    mfpTracer.setNumberOfRaysPerPoint(10);
+    mfpTracer.setRngSeed(1);
+    mfpTracer.apply();
+    VC_TEST_ASSERT(!mfpTracer.getRayTraceInfo().error);
+    VC_TEST_ASSERT(mfpTracer.getRayTraceInfo().particleHits > 0);
+  }
 
   // host-side hooks cannot run on the device: explicit error, no fallback
   TraceDisk<float, 3> userTracer;

@@ -31,24 +31,28 @@ def turned_trench(source_dir):
     return np.ascontiguousarray(pts), np.ascontiguousarray(nrm), gd
 
 
-def run_pair(c, num, max_refl=0xFFFFFFFF, max_bhits=1000, primary_dir=None):
+def run_pair(c, num, max_refl=0xFFFFFFFF, max_bhits=1000, primary_dir=None, mfp=0.0, wdist=False):
     orc = common.make_oracle(c)
     ctx, src, _ = common.make_gpu(c, primary_dir=primary_dir)
-    fo, io = orc.trace(common.oracle_particle(c),
+    po_part = common.oracle_particle(c)
+    po_part.meanFreePath = mfp
+    g_part = common.gpu_particle(c)
+    g_part.meanFreePath = mfp
+    fo, io = orc.trace(po_part,
                        orc.config(num, SEED, max_reflections=max_refl, max_boundary_hits=max_bhits,
-                                  primary_dir=primary_dir))
-    ctx.trace_device(src, [common.gpu_particle(c)],
-                     host.config(num, SEED, max_reflections=max_refl, max_boundary_hits=max_bhits),
-                     sync=True)
+                                  primary_dir=primary_dir, wdist=wdist))
+    ctx.trace_device(src, [g_part],
+                     host.config(num, SEED, max_reflections=max_refl, max_boundary_hits=max_bhits,
+                                 wdist=wdist), sync=True)
     fg = ctx.flux_download_fixed()[0]
     ig = ctx.flux_download()[1][0]
     ctx.close()
     d = io.as_dict()
     assert (fg == fo).all(), "%d primitives differ" % int((fg != fo).sum())
     assert (ig.totalRaysTraced, ig.geometryHits, ig.nonGeometryHits, ig.boundaryHits,
-            ig.reflections, ig.raysTerminated) == \
+            ig.reflections, ig.raysTerminated, ig.particleHits) == \
         (d["totalTraces"], d["geoHits"], d["nonGeoHits"], d["boundaryHits"], d["reflections"],
-         d["raysTerminated"])
+         d["raysTerminated"], d["particleHits"])
     return d
 
 
@@ -112,3 +116,26 @@ def test_triangles_matrix(bc_pair, pname):
     kind, st, pw, cone = PARTICLES[pname]
     c.update(bc=[bc_pair[0], bc_pair[1], 2], kind=kind, sticking=st, power=pw, cone=cone)
     run_pair(c, 40000)
+
+
+@pytest.mark.parametrize("mfp", [2.0, 20.0])
+@pytest.mark.parametrize("name,bc", [("trench", [1, 1, 2]), ("trench", [0, 2, 2]), ("disk2D", [1, 2, 2]),
+                                     ("triangle3D", [0, 0, 2])])
+def test_mean_free_path_scattering(name, bc, mfp):
+    """rayTraceKernel.hpp:179-203: scatter draws, particleHits counter."""
+    c = common.case(name)
+    c["bc"] = bc
+    d = run_pair(c, 50000, mfp=mfp)
+    assert d["particleHits"] > 0
+
+
+@pytest.mark.parametrize("name,pname", [("trench", "diffuse"), ("trench", "coned"), ("holes", "specular"),
+                                        ("disk2D", "diffuse")])
+def test_distance_weighted_spread(name, pname):
+    """VIENNARAY_USE_WDIST (rayTraceKernel.hpp:258-296)."""
+    c = common.case(name)
+    kind, st, pw, cone = PARTICLES[pname]
+    c.update(kind=kind, sticking=st, power=pw, cone=cone)
+    run_pair(c, 60000, wdist=True)
+    # and both options together
+    run_pair(c, 30000, wdist=True, mfp=10.0)

@@ -14,6 +14,7 @@ FLUX_FIXED_SCALE = float(2**30)
 
 PARTICLE_DIFFUSE, PARTICLE_SPECULAR, PARTICLE_CONED_COSINE = 0, 1, 2
 BOUNDARY_REFLECTIVE, BOUNDARY_PERIODIC, BOUNDARY_IGNORE = 0, 1, 2
+FLAG_WDIST = 1
 
 EXPORTS = [
     "vr_ctx_create", "vr_ctx_destroy", "vr_last_error", "vr_scene_set_disks",
@@ -37,13 +38,13 @@ class SourceDesc(C.Structure):
 
 class ParticleDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("sticking", C.c_float), ("sourcePower", C.c_float),
-                ("coneMinAngle", C.c_float)]
+                ("coneMinAngle", C.c_float), ("meanFreePath", C.c_float)]
 
 
 class Config(C.Structure):
     _fields_ = [("numRays", C.c_uint64), ("rayIdxBegin", C.c_uint64), ("rayIdxEnd", C.c_uint64),
                 ("seed", C.c_uint32), ("maxReflections", C.c_uint32),
-                ("maxBoundaryHits", C.c_uint32), ("reserved", C.c_uint32)]
+                ("maxBoundaryHits", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class TraceInfo(C.Structure):

@@ -657,6 +657,7 @@ static int fillParams(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_
   p.stream = (uint32_t)particleIndex;
   p.maxReflections = cfg->maxReflections;
   p.maxBoundaryHits = cfg->maxBoundaryHits;
+  p.flags = cfg->flags;
   p.pool = ctx->pool;
   p.poolOut = ctx->pool2;
   p.compact = 0;

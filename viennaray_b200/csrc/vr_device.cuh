@@ -329,6 +329,24 @@ __device__ __forceinline__ bool checkLocal(const float4 P, const float4 N, const
   return P.w > distance;
 }
 
+// checkLocalIntersection with the impact distance handed out (WDIST)
+__device__ __forceinline__ bool checkLocalDist(const float4 P, const float4 N, const V3 &org,
+                                               const V3 &dir, float &distance) {
+  float prod = dot3(N.x, N.y, N.z, dir.x, dir.y, dir.z);
+  if (prod > 0.f)
+    return false;
+  if (fabsf(prod) < 1e-6f)
+    return false;
+  float ddneg = dot3(P.x, P.y, P.z, N.x, N.y, N.z);
+  float tt = (ddneg - dot3(N.x, N.y, N.z, org.x, org.y, org.z)) / prod;
+  if (tt <= 0.f)
+    return false;
+  float hx = (org.x + dir.x * tt) - P.x, hy = (org.y + dir.y * tt) - P.y,
+        hz = (org.z + dir.z * tt) - P.z;
+  distance = sqrtf(dot3(hx, hy, hz, hx, hy, hz));
+  return P.w > distance;
+}
+
 // rayUtil.hpp:204-215 fillRayDirection<D>
 template <int D> __device__ __forceinline__ V3 fillDir(const V3 &direction) {
   V3 r = direction;

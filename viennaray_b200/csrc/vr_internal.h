@@ -82,6 +82,7 @@ struct TraceParams {
   uint64_t idxBegin, idxEnd;
   uint32_t seed, stream;
   uint32_t maxReflections, maxBoundaryHits;
+  uint32_t flags;  // VR_FLAG_*
   uint32_t numSlots;             // upper bound of the slots in use (sizes the grid)
   const unsigned int *slotCount; // device: slots actually in use
   unsigned long long *flux;      // numPrims fixed-point sums (internal order)

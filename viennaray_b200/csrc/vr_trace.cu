@@ -29,6 +29,7 @@ namespace vr {
 #ifndef VR_TRAV_BLOCKS
 #define VR_TRAV_BLOCKS 8
 #endif
+#define VR_WDIST_CAP 64  // disks one ray can hit at once (hit disk + its neighbour list)
 #ifndef VR_SHADE_BLOCKS
 #define VR_SHADE_BLOCKS 4
 #endif
@@ -448,14 +449,17 @@ cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s) {
 // shade: rayTraceKernel.hpp:169-333 for the hit of every live slot, then
 // regeneration of finished slots
 // ---------------------------------------------------------------------------
-template <int D, int GEO>
+// EXT == 1 adds the two optional features that are off in the default
+// instantiation: mean-free-path scattering (rayTraceKernel.hpp:179-203) and the
+// distance-weighted neighbour spread of VIENNARAY_USE_WDIST (:258-296).
+template <int D, int GEO, int EXT>
 __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t numSlots = *p.slotCount;
 
   unsigned cTraces = 0, cMiss = 0, cGeo = 0, cBnd = 0, cRefl = 0, cTerm = 0, wNb = 0, wFlux = 0;
-  unsigned wSky = 0;
+  unsigned wSky = 0, cScatter = 0;
   bool live = false, finish = false;
   float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
   if (s < numSlots)
@@ -495,7 +499,31 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
     rs = __ldcs(&p.pool.rng[s]);  // issued with the other pool loads, not after the neighbour gathers
 
     ++cTraces;
-    if (hgeom == VR_INVALID_ID) {  // :172
+    bool scattered = false;
+    if (EXT && hgeom != VR_INVALID_ID && p.particle.meanFreePath > 0.f) {  // :179-203
+      rng.load(rs, p.seed, p.stream, idx);
+      rngLoaded = true;
+      const float scatterProbability =
+          1.f - exp2det((-ht / p.particle.meanFreePath) * 1.4426950216293335f);
+      const float rnd = rng.f();
+      if (rnd < scatterProbability) {
+        org = {org.x + dir.x * rnd, org.y + dir.y * rnd, org.z + dir.z * rnd};  // sic, :188-190
+        float x, y, s2;  // pickRandomPointOnUnitSphere, rayUtil.hpp:266-283
+        do {
+          x = 2.f * rng.f() - 1.f;
+          y = 2.f * rng.f() - 1.f;
+          s2 = x * x + y * y;
+        } while (s2 >= 1.f);
+        const float tmp = 2.f * sqrtf(1.f - s2);
+        rayDirection = {x * tmp, y * tmp, 1.f - 2.f * s2};
+        dir = fillDir<D>(rayDirection);
+        ++cScatter;
+        scattered = true;
+      }
+    }
+    if (scattered) {
+      // the ray goes on from the scatter point
+    } else if (hgeom == VR_INVALID_ID) {  // :172
       ++cMiss;
       finish = true;
     } else if (hgeom == 0u) {  // :206-214
@@ -520,36 +548,71 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
         }
       } else {
         ++cGeo;
-        const unsigned long long wf = toFixed(w);
-        atomicAdd(&p.flux[hprim], wf);  // :297-306 surfaceCollision
-        ++wFlux;
-        if (GEO == 0) {  // :271-280 neighbour spread
+        if (EXT && GEO == 0 && (p.flags & VR_FLAG_WDIST)) {
+          // :258-296 every hit disk gets w / d_i / sum(1/d) * numDisksHit, d = distance of
+          // the impact point to the disk centre (+ 1e-6)
+          uint32_t ids[VR_WDIST_CAP];
+          float dist[VR_WDIST_CAP];
+          uint32_t nh = 1;
+          ids[0] = hprim;
+          {
+            const float4 P0 = __ldg(&sc.prim[2 * hprim]);
+            const float qx = hitPoint.x - P0.x, qy = hitPoint.y - P0.y, qz = hitPoint.z - P0.z;
+            dist[0] = sqrtf(dot3(qx, qy, qz, qx, qy, qz)) + 1e-6f;
+          }
           const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
-          // four neighbours per round: all index loads, then all disk loads,
-          // then the tests, so the gathers overlap
-          for (uint32_t k = k0; k < k1; k += 4) {
-            uint32_t id[4];
-            float4 P[4], Nn[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (id[j] != VR_INVALID_ID)
-                ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (id[j] != VR_INVALID_ID) {
-                ++wNb;
-                if (checkLocal(P[j], Nn[j], org, dir)) {
-                  atomicAdd(&p.flux[id[j]], wf);
-                  ++wFlux;
+          for (uint32_t k = k0; k < k1; ++k) {
+            const uint32_t id = __ldg(&sc.nbIdx[k]);
+            float4 P, Nn;
+            ldg256(&sc.prim[2 * id], P, Nn);
+            float dd;
+            ++wNb;
+            if (checkLocalDist(P, Nn, org, dir, dd) && nh < VR_WDIST_CAP) {
+              ids[nh] = id;
+              dist[nh++] = dd + 1e-6f;
+            }
+          }
+          float invSum = 0.f;
+          for (uint32_t k = 0; k < nh; ++k)
+            invSum += 1.f / dist[k];
+          for (uint32_t k = 0; k < nh; ++k) {
+            atomicAdd(&p.flux[ids[k]], toFixed(((w / dist[k]) / invSum) * (float)nh));
+            ++wFlux;
+          }
+        } else {
+          const unsigned long long wf = toFixed(w);
+          atomicAdd(&p.flux[hprim], wf);  // :297-306 surfaceCollision
+          ++wFlux;
+          if (GEO == 0) {  // :271-280 neighbour spread
+            const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
+            // four neighbours per round: all index loads, then all disk loads,
+            // then the tests, so the gathers overlap
+            for (uint32_t k = k0; k < k1; k += 4) {
+              uint32_t id[4];
+              float4 P[4], Nn[4];
+  #pragma unroll
+              for (int j = 0; j < 4; ++j)
+                id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
+  #pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (id[j] != VR_INVALID_ID)
+                  ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (id[j] != VR_INVALID_ID) {
+                  ++wNb;
+                  if (checkLocal(P[j], Nn[j], org, dir)) {
+                    atomicAdd(&p.flux[id[j]], wf);
+                    ++wFlux;
+                  }
                 }
-              }
+            }
           }
         }
-        rng.load(rs, p.seed, p.stream, idx);
-        rngLoaded = true;
+        if (!rngLoaded) {
+          rng.load(rs, p.seed, p.stream, idx);
+          rngLoaded = true;
+        }
         const V3 newDir = surfaceReflection<D>(p.particle, rayDirection, gn, rng);  // :310
         w -= w * p.particle.sticking;                                               // :316
         if (w <= 0.f) {
@@ -572,7 +635,8 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
             dir = fillDir<D>(rayDirection);
           }
         }
-        if (D == 3 && !finish && sc.sky != nullptr) {
+        if (D == 3 && !finish && sc.sky != nullptr &&
+            !(EXT && p.particle.meanFreePath > 0.f)) {  // the boundary walk would need the scatter draws
           // boundary hit of the reflected ray (needed anyway); if the sky map proves
           // that the ray meets no primitive, walk it through the boundary to its
           // end right here: it never needs a traversal
@@ -604,8 +668,6 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
             }
           }
         }
-        if (!finish)
-          __stcs(&p.pool.rng[s], rng.save());
       }
     }
     if (finish) {
@@ -626,6 +688,8 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
         __stcs(&p.pool.meta[s], make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
                                            boundaryHits | (hitFromBack ? 0x80000000u : 0u)));
         __stcs(&p.pool.weight[s], w);
+        if (rngLoaded)  // draws were taken from the stream
+          __stcs(&p.pool.rng[s], rng.save());
         if (D == 2)
           __stcs(&p.pool.dir3[s],
                  make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f));
@@ -677,12 +741,13 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
   const unsigned lane = threadIdx.x & 31u;
   unsigned long long *cnt =
       p.counters + (size_t)((blockIdx.x * 8u + (threadIdx.x >> 5)) % VR_COUNTER_COPIES) * 8;
-  // TraceInfo words: 1 traces, 2 misses, 3 geometry hits, 5 boundary hits, 6 reflections,
-  // 7 terminated
-  const unsigned vals[7] = {stillLive ? 1u : 0u, cTraces, cMiss, cGeo, cBnd, cRefl, cTerm};
-  const int wordOf[7] = {0, 1, 2, 3, 5, 6, 7};
+  // TraceInfo words: 1 traces, 2 misses, 3 geometry hits, 4 particle (scatter) hits,
+  // 5 boundary hits, 6 reflections, 7 terminated
+  const unsigned vals[8] = {stillLive ? 1u : 0u, cTraces, cMiss, cGeo, cBnd, cRefl, cTerm,
+                            cScatter};
+  const int wordOf[8] = {0, 1, 2, 3, 5, 6, 7, 4};
 #pragma unroll
-  for (int k = 0; k < 7; ++k) {
+  for (int k = 0; k < (EXT ? 8 : 7); ++k) {
     const unsigned v = __reduce_add_sync(0xffffffffu, vals[k]);
     if (lane == 0 && v)
       atomicAdd(&cnt[wordOf[k]], (unsigned long long)v);
@@ -725,21 +790,28 @@ cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int com
   return cudaGetLastError();
 }
 
+template <int EXT> static void launchShadeExt(const TraceParams &p, unsigned grid, cudaStream_t s) {
+  if (p.scene.geoType == 0) {
+    if (p.scene.D == 2)
+      shadeKernel<2, 0, EXT><<<grid, 256, 0, s>>>(p);
+    else
+      shadeKernel<3, 0, EXT><<<grid, 256, 0, s>>>(p);
+  } else {
+    if (p.scene.D == 2)
+      shadeKernel<2, 1, EXT><<<grid, 256, 0, s>>>(p);
+    else
+      shadeKernel<3, 1, EXT><<<grid, 256, 0, s>>>(p);
+  }
+}
+
 cudaError_t launchShade(const TraceParams &p, cudaStream_t s) {
   if (p.numSlots == 0)
     return cudaSuccess;
-  unsigned grid = (p.numSlots + 255u) / 256u;
-  if (p.scene.geoType == 0) {
-    if (p.scene.D == 2)
-      shadeKernel<2, 0><<<grid, 256, 0, s>>>(p);
-    else
-      shadeKernel<3, 0><<<grid, 256, 0, s>>>(p);
-  } else {
-    if (p.scene.D == 2)
-      shadeKernel<2, 1><<<grid, 256, 0, s>>>(p);
-    else
-      shadeKernel<3, 1><<<grid, 256, 0, s>>>(p);
-  }
+  const unsigned grid = (p.numSlots + 255u) / 256u;
+  if (p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST))
+    launchShadeExt<1>(p, grid, s);
+  else
+    launchShadeExt<0>(p, grid, s);
   return cudaGetLastError();
 }
 

@@ -110,9 +110,9 @@ def source_desc(lo, hi, source_dir, primary_dir=None, use_grid=False):
 
 
 def config(num_rays, seed, idx_begin=0, idx_end=None, max_reflections=0xFFFFFFFF,
-           max_boundary_hits=1000):
+           max_boundary_hits=1000, wdist=False):
     return capi.Config(num_rays, idx_begin, num_rays if idx_end is None else idx_end, seed,
-                       max_reflections, max_boundary_hits, 0)
+                       max_reflections, max_boundary_hits, capi.FLAG_WDIST if wdist else 0)
 
 
 def triangle_normals(verts, tris):
