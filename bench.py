@@ -6,11 +6,11 @@ ion).
     python bench.py --gpus N --steps K --warmup W            # the CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm
 
-One step = one pass of the hot path over one batch of rays: `--rays` rays per
-particle per GPU (default 2.5e8, so the default K=4 steps trace the config's
-1e9 rays per particle on one GPU).  Ray indices of consecutive steps and of
-different ranks are disjoint slices of one job, so weak scaling over N GPUs is
-the same Monte Carlo estimate with N times the rays.  Prints ONE JSON line.
+One step = one pass of the hot path over the config's batch: `--rays` rays per
+particle per GPU (default 1e9, BASELINE.json's "1e9 rays" of the 1M-disk
+trench, for each of the two particles).  Ray indices of consecutive steps and
+of different ranks are disjoint slices of one job, so weak scaling over N GPUs
+is the same Monte Carlo estimate with N times the rays.  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -123,7 +123,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays", type=float, default=2.5e8, help="rays per particle per GPU per step")
+    ap.add_argument("--rays", type=float, default=1e9, help="rays per particle per GPU per step")
     ap.add_argument("--warmup-rays", type=float, default=2e7)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -764,7 +764,7 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
       if (!compact)
         batch = (int)std::min<uint64_t>(std::max<uint64_t>((shardRays - handed) / slots, 1), 256);
       else if (compacted)
-        batch = bound > 262144u ? 2 : 16;
+        batch = bound > 262144u ? 2 : (bound > 8192u ? 16 : 64);  // the long thin tail
       for (int b = 0; b < batch; ++b) {
         p.pool = cur ? ctx->pool2 : ctx->pool;
         p.poolOut = cur ? ctx->pool : ctx->pool2;

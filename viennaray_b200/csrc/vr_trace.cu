@@ -27,7 +27,7 @@ namespace vr {
 #define VR_REFILL_MIN 1  // idle lanes a warp waits for before it fetches new slots
 #endif
 #ifndef VR_TRAV_BLOCKS
-#define VR_TRAV_BLOCKS 8
+#define VR_TRAV_BLOCKS 12  // resident blocks per SM asked of ptxas (caps registers at 40)
 #endif
 #define VR_WDIST_CAP 64  // disks one ray can hit at once (hit disk + its neighbour list)
 #ifndef VR_SHADE_BLOCKS
