@@ -49,11 +49,16 @@ __device__ __noinline__ void boundaryTest(const DeviceScene &sc, const V3 &org, 
   // margin of the cheap rectangle check, in length units
   const float ext = fmaxf(fmaxf(sc.bbox[1][0] - sc.bbox[0][0], sc.bbox[1][1] - sc.bbox[0][1]),
                           sc.bbox[1][2] - sc.bbox[0][2]);
-#pragma unroll 1
+  // 1. all lanes together: which of the four planes can the ray hit inside the
+  //    box face?  (usually one.)  Their plane distances select the order.
+  float tpk[4];
+  unsigned cand = 0u;
+#pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int axis = k < 2 ? sc.firstDir : sc.secondDir;
     const float c = sc.bbox[k & 1][axis];
     const float da = comp(dir, axis);
+    tpk[k] = 3.402823466e+38f;
     if (da == 0.f)
       continue;
     const float tp = (c - comp(org, axis)) / da;
@@ -67,6 +72,24 @@ __device__ __noinline__ void boundaryTest(const DeviceScene &sc, const V3 &org, 
         (axis != 1 && (hy < sc.bbox[0][1] - m || hy > sc.bbox[1][1] + m)) ||
         (axis != 2 && (hz < sc.bbox[0][2] - m || hz > sc.bbox[1][2] + m)))
       continue;
+    tpk[k] = tp;
+    cand |= 1u << k;
+  }
+  // 2. the exact triangle tests, nearest candidate plane first; the lanes of a warp run
+  //    this loop side by side on their own planes instead of idling through a loop over
+  //    all four (that loop ran the tests with ~2 active lanes)
+  while (cand) {
+    int k = 0;
+    float tmin = 3.402823466e+38f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if ((cand >> q & 1u) && tpk[q] < tmin) {
+        tmin = tpk[q];
+        k = q;
+      }
+    cand &= ~(1u << k);
+    if (!(tmin <= best.t * 1.00001f + 1e-5f))
+      break;  // the remaining planes lie behind the hit that was found
 #pragma unroll 1
     for (int j = 0; j < 2; ++j) {
       const int i = 2 * k + j;
