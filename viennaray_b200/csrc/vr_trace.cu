@@ -44,8 +44,11 @@ __device__ __forceinline__ bool slotEmpty(const float4 &od0) { return od0.w != o
 // Not inlined and not unrolled on purpose: the shade kernel calls it from several
 // places, and eight inlined triangle tests per call site pushed that kernel to
 // 123 KB of SASS (instruction-fetch stalls were 23 % of its samples).
-__device__ __noinline__ void boundaryTest(const DeviceScene &sc, const V3 &org, const V3 &dir,
-                                          Hit &best) {
+// (arguments and result by value: a real call that keeps everything in registers)
+__device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, const V3 dir) {
+  Hit best;
+  best.t = 3.402823466e+38f;
+  best.geom = best.prim = best.orig = VR_INVALID_ID;
   // margin of the cheap rectangle check, in length units
   const float ext = fmaxf(fmaxf(sc.bbox[1][0] - sc.bbox[0][0], sc.bbox[1][1] - sc.bbox[0][1]),
                           sc.bbox[1][2] - sc.bbox[0][2]);
@@ -99,15 +102,13 @@ __device__ __noinline__ void boundaryTest(const DeviceScene &sc, const V3 &org, 
       testTri(v0, v1, v2, 0u, (uint32_t)i, (uint32_t)i, org, dir, best, nullptr);
     }
   }
+  return best;
 }
 
 // closest boundary hit of a fresh ray, stored as the traversal's initial best
 __device__ __forceinline__ void storeBoundaryHit(const DeviceScene &sc, const RayPool &pool,
                                                  uint32_t s, const V3 &org, const V3 &dir) {
-  Hit best;
-  best.t = 3.402823466e+38f;
-  best.geom = best.prim = best.orig = VR_INVALID_ID;
-  boundaryTest(sc, org, dir, best);
+  const Hit best = boundaryTest(sc, org, dir);
   __stcs(&pool.hit[s],
          make_float4(best.t, __uint_as_float(best.prim), __uint_as_float(best.geom), 0.f));
 }
@@ -472,47 +473,265 @@ cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s) {
 // shade: rayTraceKernel.hpp:169-333 for the hit of every live slot, then
 // regeneration of finished slots
 // ---------------------------------------------------------------------------
+// The state of one ray while its hit is processed, and the per-thread tallies.
+struct RayState {
+  V3 org, dir, rayDirection;
+  float w;
+  uint64_t idx;
+  uint32_t numReflections, boundaryHits;
+  bool hitFromBack;
+  bool rngLoaded;  // rng holds the ray's stream (else it still sits in rs as loaded from the pool)
+  bool bhValid;    // bh is the boundary hit of the ray as it stands after the call
+  Hit bh;
+  Rng rng;
+  uint4 rs;
+};
+struct Tally {
+  unsigned cTraces, cMiss, cGeo, cBnd, cRefl, cTerm, wNb, wFlux, wSky, cScatter;
+};
+
+// What rayTraceKernel.hpp:169-333 does with the hit (t, prim, geom) of a ray: miss,
+// boundary handling, back-face rule, neighbour spread, particle functor, roulette, and
+// the sky map's shortcut for rays that leave the scene.  Returns true when the ray ended.
 // EXT == 1 adds the two optional features that are off in the default
 // instantiation: mean-free-path scattering (rayTraceKernel.hpp:179-203) and the
 // distance-weighted neighbour spread of VIENNARAY_USE_WDIST (:258-296).
+template <int D, int GEO, int EXT>
+__device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, const float ht,
+                                         const uint32_t hprim, const uint32_t hgeom, Tally &c) {
+  const DeviceScene &sc = p.scene;
+  V3 &org = r.org, &dir = r.dir, &rayDirection = r.rayDirection;
+  float &w = r.w;
+  const uint64_t idx = r.idx;
+  uint32_t &numReflections = r.numReflections, &boundaryHits = r.boundaryHits;
+  bool &hitFromBack = r.hitFromBack, &rngLoaded = r.rngLoaded, &bhValid = r.bhValid;
+  Hit &bh = r.bh;
+  Rng &rng = r.rng;
+  const uint4 rs = r.rs;
+  unsigned &cTraces = c.cTraces, &cMiss = c.cMiss, &cGeo = c.cGeo, &cBnd = c.cBnd,
+           &cRefl = c.cRefl, &cTerm = c.cTerm, &wNb = c.wNb, &wFlux = c.wFlux, &wSky = c.wSky,
+           &cScatter = c.cScatter;
+  bool finish = false;
+  bhValid = false;
+  ++cTraces;
+  bool scattered = false;
+  if (EXT && hgeom != VR_INVALID_ID && p.particle.meanFreePath > 0.f) {  // :179-203
+    rng.load(rs, p.seed, p.stream, idx);
+    rngLoaded = true;
+    const float scatterProbability =
+        1.f - exp2det((-ht / p.particle.meanFreePath) * 1.4426950216293335f);
+    const float rnd = rng.f();
+    if (rnd < scatterProbability) {
+      org = {org.x + dir.x * rnd, org.y + dir.y * rnd, org.z + dir.z * rnd};  // sic, :188-190
+      float x, y, s2;  // pickRandomPointOnUnitSphere, rayUtil.hpp:266-283
+      do {
+        x = 2.f * rng.f() - 1.f;
+        y = 2.f * rng.f() - 1.f;
+        s2 = x * x + y * y;
+      } while (s2 >= 1.f);
+      const float tmp = 2.f * sqrtf(1.f - s2);
+      rayDirection = {x * tmp, y * tmp, 1.f - 2.f * s2};
+      dir = fillDir<D>(rayDirection);
+      ++cScatter;
+      scattered = true;
+    }
+  }
+  if (scattered) {
+    // the ray goes on from the scatter point
+  } else if (hgeom == VR_INVALID_ID) {  // :172
+    ++cMiss;
+    finish = true;
+  } else if (hgeom == 0u) {  // :206-214
+    if (++boundaryHits > p.maxBoundaryHits) {
+      ++cTerm;
+      finish = true;
+    } else if (!boundaryHit<D>(sc, org, rayDirection, dir, hprim, ht)) {
+      finish = true;
+    }
+  } else {
+    const V3 hitPoint = {org.x + dir.x * ht, org.y + dir.y * ht, org.z + dir.z * ht};
+    const float4 N4 = __ldg(&sc.prim[GEO == 0 ? 2 * hprim + 1 : 4 * hprim + 3]);
+    const V3 gn = {N4.x, N4.y, N4.z};
+    const bool backface = dot(rayDirection, gn) > 0.f;  // :224
+    if (backface) {
+      if (GEO == 0 && !hitFromBack) {  // :226-241 let the ray through once
+        hitFromBack = true;
+        org = hitPoint;
+      } else {
+        ++cTerm;
+        finish = true;
+      }
+    } else {
+      ++cGeo;
+      if (EXT && GEO == 0 && (p.flags & VR_FLAG_WDIST)) {
+        // :258-296 every hit disk gets w / d_i / sum(1/d) * numDisksHit, d = distance of
+        // the impact point to the disk centre (+ 1e-6)
+        uint32_t ids[VR_WDIST_CAP];
+        float dist[VR_WDIST_CAP];
+        uint32_t nh = 1;
+        ids[0] = hprim;
+        {
+          const float4 P0 = __ldg(&sc.prim[2 * hprim]);
+          const float qx = hitPoint.x - P0.x, qy = hitPoint.y - P0.y, qz = hitPoint.z - P0.z;
+          dist[0] = sqrtf(dot3(qx, qy, qz, qx, qy, qz)) + 1e-6f;
+        }
+        const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
+        for (uint32_t k = k0; k < k1; ++k) {
+          const uint32_t id = __ldg(&sc.nbIdx[k]);
+          float4 P, Nn;
+          ldg256(&sc.prim[2 * id], P, Nn);
+          float dd;
+          ++wNb;
+          if (checkLocalDist(P, Nn, org, dir, dd) && nh < VR_WDIST_CAP) {
+            ids[nh] = id;
+            dist[nh++] = dd + 1e-6f;
+          }
+        }
+        float invSum = 0.f;
+        for (uint32_t k = 0; k < nh; ++k)
+          invSum += 1.f / dist[k];
+        for (uint32_t k = 0; k < nh; ++k) {
+          atomicAdd(&p.flux[ids[k]], toFixed(((w / dist[k]) / invSum) * (float)nh));
+          ++wFlux;
+        }
+      } else {
+        const unsigned long long wf = toFixed(w);
+        atomicAdd(&p.flux[hprim], wf);  // :297-306 surfaceCollision
+        ++wFlux;
+        if (GEO == 0) {  // :271-280 neighbour spread
+          const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
+          // four neighbours per round: all index loads, then all disk loads,
+          // then the tests, so the gathers overlap
+          for (uint32_t k = k0; k < k1; k += 4) {
+            uint32_t id[4];
+            float4 P[4], Nn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (id[j] != VR_INVALID_ID)
+                ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (id[j] != VR_INVALID_ID) {
+                ++wNb;
+                if (checkLocal(P[j], Nn[j], org, dir)) {
+                  atomicAdd(&p.flux[id[j]], wf);
+                  ++wFlux;
+                }
+              }
+          }
+        }
+      }
+      if (!rngLoaded) {
+        rng.load(rs, p.seed, p.stream, idx);
+        rngLoaded = true;
+      }
+      const V3 newDir = surfaceReflection<D>(p.particle, rayDirection, gn, rng);  // :310
+      w -= w * p.particle.sticking;                                               // :316
+      if (w <= 0.f) {
+        finish = true;
+      } else if (++numReflections > p.maxReflections) {
+        ++cTerm;
+        finish = true;
+      } else {
+        // :435-460 rejectionControl, thresholds 0.1 / 0.3 of the initial weight
+        if (w < 0.1f) {
+          const float kill = 1.f - w / 0.3f;
+          if (rng.f() < kill)
+            finish = true;
+          else
+            w = 0.3f;
+        }
+        if (!finish) {
+          rayDirection = newDir;
+          org = hitPoint;
+          dir = fillDir<D>(rayDirection);
+        }
+      }
+      if (D == 3 && !finish && sc.sky != nullptr &&
+          !(EXT && p.particle.meanFreePath > 0.f)) {  // the boundary walk would need the scatter draws
+        // boundary hit of the reflected ray (needed anyway); if the sky map proves
+        // that the ray meets no primitive, walk it through the boundary to its
+        // end right here: it never needs a traversal
+        bh = boundaryTest(sc, org, dir);
+        bhValid = true;
+        if (skyEscapes(sc, org, dir, bh.t)) {
+          ++wSky;
+          for (;;) {
+            ++cTraces;
+            if (bh.geom == VR_INVALID_ID) {
+              ++cMiss;
+              finish = true;
+              break;
+            }
+            if (++boundaryHits > p.maxBoundaryHits) {
+              ++cTerm;
+              finish = true;
+              break;
+            }
+            if (!boundaryHit<D>(sc, org, rayDirection, dir, bh.prim, bh.t)) {
+              finish = true;
+              break;
+            }
+            bh = boundaryTest(sc, org, dir);
+          }
+        }
+      }
+    }
+  }
+  if (finish) {
+    cBnd += boundaryHits;
+    cRefl += numReflections;
+  }
+  return finish;
+}
+
 template <int D, int GEO, int EXT>
 __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t numSlots = *p.slotCount;
 
-  unsigned cTraces = 0, cMiss = 0, cGeo = 0, cBnd = 0, cRefl = 0, cTerm = 0, wNb = 0, wFlux = 0;
-  unsigned wSky = 0, cScatter = 0;
+  Tally c = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   bool live = false, finish = false;
   float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
   if (s < numSlots)
     a = __ldcs(&p.pool.od0[s]);
   live = !slotEmpty(a);
 
-  V3 org = {a.x, a.y, a.z}, dir = {0.f, 0.f, 0.f}, rayDirection = {0.f, 0.f, 0.f};
-  float w = 0.f;
-  uint64_t idx = 0;
-  uint32_t numReflections = 0, boundaryHits = 0;
-  bool hitFromBack = false, rngLoaded = false, bhValid = false;
-  Hit bh;
-  bh.t = 0.f;
-  bh.geom = bh.prim = bh.orig = VR_INVALID_ID;
-  Rng rng;
-  rng.init(0, 0, 0);
-  uint4 rs = make_uint4(0u, 0u, 0u, 0u);
+  RayState r;
+  r.org = {a.x, a.y, a.z};
+  r.dir = {0.f, 0.f, 0.f};
+  r.rayDirection = {0.f, 0.f, 0.f};
+  r.w = 0.f;
+  r.idx = 0;
+  r.numReflections = r.boundaryHits = 0u;
+  r.hitFromBack = r.rngLoaded = r.bhValid = false;
+  r.bh.t = 0.f;
+  r.bh.geom = r.bh.prim = r.bh.orig = VR_INVALID_ID;
+  r.rng.init(0, 0, 0);
+  r.rs = make_uint4(0u, 0u, 0u, 0u);
+  V3 &org = r.org, &dir = r.dir, &rayDirection = r.rayDirection;
+  float &w = r.w;
+  uint64_t &idx = r.idx;
+  uint32_t &numReflections = r.numReflections, &boundaryHits = r.boundaryHits;
+  bool &hitFromBack = r.hitFromBack, &rngLoaded = r.rngLoaded, &bhValid = r.bhValid;
+  Hit &bh = r.bh;
+  Rng &rng = r.rng;
+  uint4 &rs = r.rs;
 
   if (live) {
     const float2 b = __ldcs(&p.pool.od1[s]);
     dir = {a.w, b.x, b.y};
     if (D == 2) {
-      const float4 r = __ldcs(&p.pool.dir3[s]);
-      rayDirection = {r.x, r.y, r.z};
+      const float4 d3 = __ldcs(&p.pool.dir3[s]);
+      rayDirection = {d3.x, d3.y, d3.z};
     } else {
       rayDirection = dir;
     }
     const float4 hv = __ldcs(&p.pool.hit[s]);
-    const float ht = hv.x;
-    const uint32_t hprim = __float_as_uint(hv.y), hgeom = __float_as_uint(hv.z);
     const uint4 meta = __ldcs(&p.pool.meta[s]);
     idx = (uint64_t)meta.x | ((uint64_t)meta.y << 32);
     numReflections = meta.z;
@@ -520,183 +739,7 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
     hitFromBack = (meta.w >> 31) != 0u;
     w = __ldcs(&p.pool.weight[s]);
     rs = __ldcs(&p.pool.rng[s]);  // issued with the other pool loads, not after the neighbour gathers
-
-    ++cTraces;
-    bool scattered = false;
-    if (EXT && hgeom != VR_INVALID_ID && p.particle.meanFreePath > 0.f) {  // :179-203
-      rng.load(rs, p.seed, p.stream, idx);
-      rngLoaded = true;
-      const float scatterProbability =
-          1.f - exp2det((-ht / p.particle.meanFreePath) * 1.4426950216293335f);
-      const float rnd = rng.f();
-      if (rnd < scatterProbability) {
-        org = {org.x + dir.x * rnd, org.y + dir.y * rnd, org.z + dir.z * rnd};  // sic, :188-190
-        float x, y, s2;  // pickRandomPointOnUnitSphere, rayUtil.hpp:266-283
-        do {
-          x = 2.f * rng.f() - 1.f;
-          y = 2.f * rng.f() - 1.f;
-          s2 = x * x + y * y;
-        } while (s2 >= 1.f);
-        const float tmp = 2.f * sqrtf(1.f - s2);
-        rayDirection = {x * tmp, y * tmp, 1.f - 2.f * s2};
-        dir = fillDir<D>(rayDirection);
-        ++cScatter;
-        scattered = true;
-      }
-    }
-    if (scattered) {
-      // the ray goes on from the scatter point
-    } else if (hgeom == VR_INVALID_ID) {  // :172
-      ++cMiss;
-      finish = true;
-    } else if (hgeom == 0u) {  // :206-214
-      if (++boundaryHits > p.maxBoundaryHits) {
-        ++cTerm;
-        finish = true;
-      } else if (!boundaryHit<D>(sc, org, rayDirection, dir, hprim, ht)) {
-        finish = true;
-      }
-    } else {
-      const V3 hitPoint = {org.x + dir.x * ht, org.y + dir.y * ht, org.z + dir.z * ht};
-      const float4 N4 = __ldg(&sc.prim[GEO == 0 ? 2 * hprim + 1 : 4 * hprim + 3]);
-      const V3 gn = {N4.x, N4.y, N4.z};
-      const bool backface = dot(rayDirection, gn) > 0.f;  // :224
-      if (backface) {
-        if (GEO == 0 && !hitFromBack) {  // :226-241 let the ray through once
-          hitFromBack = true;
-          org = hitPoint;
-        } else {
-          ++cTerm;
-          finish = true;
-        }
-      } else {
-        ++cGeo;
-        if (EXT && GEO == 0 && (p.flags & VR_FLAG_WDIST)) {
-          // :258-296 every hit disk gets w / d_i / sum(1/d) * numDisksHit, d = distance of
-          // the impact point to the disk centre (+ 1e-6)
-          uint32_t ids[VR_WDIST_CAP];
-          float dist[VR_WDIST_CAP];
-          uint32_t nh = 1;
-          ids[0] = hprim;
-          {
-            const float4 P0 = __ldg(&sc.prim[2 * hprim]);
-            const float qx = hitPoint.x - P0.x, qy = hitPoint.y - P0.y, qz = hitPoint.z - P0.z;
-            dist[0] = sqrtf(dot3(qx, qy, qz, qx, qy, qz)) + 1e-6f;
-          }
-          const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
-          for (uint32_t k = k0; k < k1; ++k) {
-            const uint32_t id = __ldg(&sc.nbIdx[k]);
-            float4 P, Nn;
-            ldg256(&sc.prim[2 * id], P, Nn);
-            float dd;
-            ++wNb;
-            if (checkLocalDist(P, Nn, org, dir, dd) && nh < VR_WDIST_CAP) {
-              ids[nh] = id;
-              dist[nh++] = dd + 1e-6f;
-            }
-          }
-          float invSum = 0.f;
-          for (uint32_t k = 0; k < nh; ++k)
-            invSum += 1.f / dist[k];
-          for (uint32_t k = 0; k < nh; ++k) {
-            atomicAdd(&p.flux[ids[k]], toFixed(((w / dist[k]) / invSum) * (float)nh));
-            ++wFlux;
-          }
-        } else {
-          const unsigned long long wf = toFixed(w);
-          atomicAdd(&p.flux[hprim], wf);  // :297-306 surfaceCollision
-          ++wFlux;
-          if (GEO == 0) {  // :271-280 neighbour spread
-            const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
-            // four neighbours per round: all index loads, then all disk loads,
-            // then the tests, so the gathers overlap
-            for (uint32_t k = k0; k < k1; k += 4) {
-              uint32_t id[4];
-              float4 P[4], Nn[4];
-  #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
-  #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (id[j] != VR_INVALID_ID)
-                  ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
-  #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (id[j] != VR_INVALID_ID) {
-                  ++wNb;
-                  if (checkLocal(P[j], Nn[j], org, dir)) {
-                    atomicAdd(&p.flux[id[j]], wf);
-                    ++wFlux;
-                  }
-                }
-            }
-          }
-        }
-        if (!rngLoaded) {
-          rng.load(rs, p.seed, p.stream, idx);
-          rngLoaded = true;
-        }
-        const V3 newDir = surfaceReflection<D>(p.particle, rayDirection, gn, rng);  // :310
-        w -= w * p.particle.sticking;                                               // :316
-        if (w <= 0.f) {
-          finish = true;
-        } else if (++numReflections > p.maxReflections) {
-          ++cTerm;
-          finish = true;
-        } else {
-          // :435-460 rejectionControl, thresholds 0.1 / 0.3 of the initial weight
-          if (w < 0.1f) {
-            const float kill = 1.f - w / 0.3f;
-            if (rng.f() < kill)
-              finish = true;
-            else
-              w = 0.3f;
-          }
-          if (!finish) {
-            rayDirection = newDir;
-            org = hitPoint;
-            dir = fillDir<D>(rayDirection);
-          }
-        }
-        if (D == 3 && !finish && sc.sky != nullptr &&
-            !(EXT && p.particle.meanFreePath > 0.f)) {  // the boundary walk would need the scatter draws
-          // boundary hit of the reflected ray (needed anyway); if the sky map proves
-          // that the ray meets no primitive, walk it through the boundary to its
-          // end right here: it never needs a traversal
-          bh.t = 3.402823466e+38f;
-          bh.geom = bh.prim = bh.orig = VR_INVALID_ID;
-          boundaryTest(sc, org, dir, bh);
-          bhValid = true;
-          if (skyEscapes(sc, org, dir, bh.t)) {
-            ++wSky;
-            for (;;) {
-              ++cTraces;
-              if (bh.geom == VR_INVALID_ID) {
-                ++cMiss;
-                finish = true;
-                break;
-              }
-              if (++boundaryHits > p.maxBoundaryHits) {
-                ++cTerm;
-                finish = true;
-                break;
-              }
-              if (!boundaryHit<D>(sc, org, rayDirection, dir, bh.prim, bh.t)) {
-                finish = true;
-                break;
-              }
-              bh.t = 3.402823466e+38f;
-              bh.geom = bh.prim = bh.orig = VR_INVALID_ID;
-              boundaryTest(sc, org, dir, bh);
-            }
-          }
-        }
-      }
-    }
-    if (finish) {
-      cBnd += boundaryHits;
-      cRefl += numReflections;
-    }
+    finish = shadeHit<D, GEO, EXT>(p, r, hv.x, __float_as_uint(hv.y), __float_as_uint(hv.z), c);
   }
 
   // ---- regenerate finished slots; write survivors back (in place, or appended to
@@ -766,8 +809,8 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
       p.counters + (size_t)((blockIdx.x * 8u + (threadIdx.x >> 5)) % VR_COUNTER_COPIES) * 8;
   // TraceInfo words: 1 traces, 2 misses, 3 geometry hits, 4 particle (scatter) hits,
   // 5 boundary hits, 6 reflections, 7 terminated
-  const unsigned vals[8] = {stillLive ? 1u : 0u, cTraces, cMiss, cGeo, cBnd, cRefl, cTerm,
-                            cScatter};
+  const unsigned vals[8] = {stillLive ? 1u : 0u, c.cTraces, c.cMiss, c.cGeo, c.cBnd, c.cRefl,
+                            c.cTerm, c.cScatter};
   const int wordOf[8] = {0, 1, 2, 3, 5, 6, 7, 4};
 #pragma unroll
   for (int k = 0; k < (EXT ? 8 : 7); ++k) {
@@ -776,7 +819,7 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
       atomicAdd(&cnt[wordOf[k]], (unsigned long long)v);
   }
   if (p.work) {
-    const unsigned wv[3] = {wNb, wFlux, wSky};
+    const unsigned wv[3] = {c.wNb, c.wFlux, c.wSky};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const unsigned v = __reduce_add_sync(0xffffffffu, wv[k]);
