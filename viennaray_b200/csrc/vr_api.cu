@@ -64,6 +64,7 @@ struct vr_ctx {
   float2 *dSky = nullptr;
   int skyAxis = -1;
   float skySign = 0.f, skyTop = 0.f;
+  uint32_t tailRays = 262144;  // VR_TAIL_RAYS: survivors handed to the one-launch tail kernel
   int skyCells = 128;  // VR_SKY_CELLS; 0 disables the map
   bool timeKernels = false;  // VR_TIME_KERNELS=1: CUDA events around every launch
   std::vector<cudaEvent_t> tev;
@@ -250,6 +251,11 @@ int vr_ctx_create(int cudaDevice, vr_ctx **out) {
   ctx->numSMs = prop.multiProcessorCount;
   const char *cw = getenv("VR_COUNT_WORK");
   ctx->countWork = cw && cw[0] == '1';
+  if (const char *tr = getenv("VR_TAIL_RAYS")) {
+    long v = atol(tr);
+    if (v >= 0 && v <= (1l << 24))
+      ctx->tailRays = (uint32_t)v;
+  }
   if (const char *sk = getenv("VR_SKY_CELLS")) {
     long v = atol(sk);
     if (v >= 0 && v <= 1024)
@@ -800,6 +806,17 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
       if (live < slots) {
         compact = true;
         bound = std::min(bound, live);
+      }
+      if (compacted && live <= ctx->tailRays) {
+        // the thin tail: every remaining ray is finished by one thread of one launch
+        p.pool = cur ? ctx->pool2 : ctx->pool;
+        p.numSlots = bound;
+        mark(ctx, 2);
+        CK(launchTail(p, ctx->stream));
+        mark(ctx, 1);
+        ctx->kernelLaunches += 1;
+        ++ctx->iterations;
+        break;
       }
     }
     reduceCountersKernel<<<1, 32, 0, ctx->stream>>>(ctx->dCounterCopies,

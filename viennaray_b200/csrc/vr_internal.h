@@ -144,6 +144,8 @@ cudaError_t launchTriBounds(const float4 *v0, const float4 *v1, const float4 *v2
 cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s);
 cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s);
 cudaError_t launchShade(const TraceParams &p, cudaStream_t s);
+// the last rays of a trace, each run to its end by one thread (compacted pool in p.pool)
+cudaError_t launchTail(const TraceParams &p, cudaStream_t s);
 // between iterations: resets the cursors; compact mode: slotCount = liveCount
 cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int compact,
                        cudaStream_t s);

@@ -147,6 +147,88 @@ __device__ __forceinline__ unsigned long long warpSum(unsigned long long v) {
 }
 
 // ---------------------------------------------------------------------------
+// closest hit of ONE ray by its own thread (no warp cooperation): the tail
+// kernel's traversal.  Same node / primitive tests as traverseKernel; `best`
+// comes in as the ray's boundary hit.
+// ---------------------------------------------------------------------------
+template <int GEO>
+__device__ __forceinline__ void traverseOne(const DeviceScene &sc, const V3 &org, const V3 &dir,
+                                            Hit &best, unsigned &wNodes, unsigned &wPrims) {
+  if (!sc.numPrims)
+    return;
+  float ix = 1.f / (fabsf(dir.x) > 1e-20f ? dir.x : copysignf(1e-20f, dir.x));
+  float iy = 1.f / (fabsf(dir.y) > 1e-20f ? dir.y : copysignf(1e-20f, dir.y));
+  float iz = 1.f / (fabsf(dir.z) > 1e-20f ? dir.z : copysignf(1e-20f, dir.z));
+  const float ox = (sc.qLo[0] - org.x) * ix, oy = (sc.qLo[1] - org.y) * iy,
+              oz = (sc.qLo[2] - org.z) * iz;
+  ix *= sc.qScale[0];
+  iy *= sc.qScale[1];
+  iz *= sc.qScale[2];
+  uint32_t stack[VR_STACK];
+  int sp = 0;
+  uint32_t cur = sc.rootRef;
+  while (cur != VR_DONE) {
+    if (cur < VR_DONE) {  // inner node
+      uint4 c0, c1;
+      ldg256(sc.nodes + cur, c0, c1);
+      ++wNodes;
+      const float t0x = __fmaf_rn((float)(c0.x & 0xffffu), ix, ox),
+                  t1x = __fmaf_rn((float)(c0.y >> 16), ix, ox);
+      const float t0y = __fmaf_rn((float)(c0.x >> 16), iy, oy),
+                  t1y = __fmaf_rn((float)(c0.z & 0xffffu), iy, oy);
+      const float t0z = __fmaf_rn((float)(c0.y & 0xffffu), iz, oz),
+                  t1z = __fmaf_rn((float)(c0.z >> 16), iz, oz);
+      const float n0 =
+          fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
+      const float f0 =
+          fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
+      const float u0x = __fmaf_rn((float)(c1.x & 0xffffu), ix, ox),
+                  u1x = __fmaf_rn((float)(c1.y >> 16), ix, ox);
+      const float u0y = __fmaf_rn((float)(c1.x >> 16), iy, oy),
+                  u1y = __fmaf_rn((float)(c1.z & 0xffffu), iy, oy);
+      const float u0z = __fmaf_rn((float)(c1.y & 0xffffu), iz, oz),
+                  u1z = __fmaf_rn((float)(c1.z >> 16), iz, oz);
+      const float n1 =
+          fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), VR_TNEAR));
+      const float f1 =
+          fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), best.t));
+      const bool h0 = n0 * 0.99999f <= f0 * 1.00001f + 1e-6f;
+      const bool h1 = n1 * 0.99999f <= f1 * 1.00001f + 1e-6f;
+      const uint32_t r0 = c0.w, r1 = c1.w;
+      if (h0 && h1) {
+        const bool swap = n1 < n0;
+        if (sp < VR_STACK)
+          stack[sp++] = swap ? r0 : r1;
+        cur = swap ? r1 : r0;
+      } else if (h0) {
+        cur = r0;
+      } else if (h1) {
+        cur = r1;
+      } else {
+        cur = sp ? stack[--sp] : VR_DONE;
+      }
+    } else {  // leaf
+      const uint32_t first = (cur & 0x7fffffffu) >> 4, count = cur & 15u;
+      for (uint32_t k = 0; k < count; ++k) {
+        const uint32_t i = first + k;
+        if (GEO == 0) {
+          float4 P, N;
+          ldg256(&sc.prim[2 * i], P, N);
+          testDisk(P, N, i, org, dir, best);
+        } else {
+          const float4 a = __ldg(&sc.prim[4 * i]), b = __ldg(&sc.prim[4 * i + 1]),
+                       c = __ldg(&sc.prim[4 * i + 2]);
+          testTri({a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, 1u, i, __float_as_uint(a.w),
+                  org, dir, best, nullptr);
+        }
+      }
+      wPrims += count;
+      cur = sp ? stack[--sp] : VR_DONE;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // traverse: closest hit of every live slot
 // ---------------------------------------------------------------------------
 template <int GEO>
@@ -516,8 +598,10 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, cons
   ++cTraces;
   bool scattered = false;
   if (EXT && hgeom != VR_INVALID_ID && p.particle.meanFreePath > 0.f) {  // :179-203
-    rng.load(rs, p.seed, p.stream, idx);
-    rngLoaded = true;
+    if (!rngLoaded) {
+      rng.load(rs, p.seed, p.stream, idx);
+      rngLoaded = true;
+    }
     const float scatterProbability =
         1.f - exp2det((-ht / p.particle.meanFreePath) * 1.4426950216293335f);
     const float rnd = rng.f();
@@ -827,6 +911,101 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
         atomicAdd(&p.work[2 + k], (unsigned long long)v);
     }
   }
+}
+
+// The thin tail of a trace: once the source is exhausted and only a few
+// thousand rays are left, every remaining ray is run to its end by one thread
+// of ONE launch -- traverse and shade in a loop -- instead of ~1000 iterations
+// of three tiny launches each.  Same arithmetic, same tallies.
+template <int D, int GEO, int EXT>
+__global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ TraceParams p) {
+  const DeviceScene &sc = p.scene;
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t numSlots = *p.slotCount;
+  Tally c = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  unsigned wNodes = 0, wPrims = 0;
+  float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
+  if (s < numSlots)
+    a = __ldcs(&p.pool.od0[s]);
+  if (!slotEmpty(a)) {
+    RayState r;
+    const float2 b = __ldcs(&p.pool.od1[s]);
+    r.org = {a.x, a.y, a.z};
+    r.dir = {a.w, b.x, b.y};
+    if (D == 2) {
+      const float4 d3 = __ldcs(&p.pool.dir3[s]);
+      r.rayDirection = {d3.x, d3.y, d3.z};
+    } else {
+      r.rayDirection = r.dir;
+    }
+    const float4 hv = __ldcs(&p.pool.hit[s]);
+    const uint4 meta = __ldcs(&p.pool.meta[s]);
+    r.idx = (uint64_t)meta.x | ((uint64_t)meta.y << 32);
+    r.numReflections = meta.z;
+    r.boundaryHits = meta.w & 0x7fffffffu;
+    r.hitFromBack = (meta.w >> 31) != 0u;
+    r.w = __ldcs(&p.pool.weight[s]);
+    r.rs = __ldcs(&p.pool.rng[s]);
+    r.rngLoaded = false;
+    r.rng.init(0, 0, 0);
+    r.bhValid = true;  // the pool holds the ray's boundary hit
+    r.bh.t = hv.x;
+    r.bh.prim = r.bh.orig = __float_as_uint(hv.y);
+    r.bh.geom = __float_as_uint(hv.z);
+    for (;;) {
+      if (!r.bhValid)
+        r.bh = boundaryTest(sc, r.org, r.dir);
+      Hit best = r.bh;
+      traverseOne<GEO>(sc, r.org, r.dir, best, wNodes, wPrims);
+      if (shadeHit<D, GEO, EXT>(p, r, best.t, best.prim, best.geom, c))
+        break;
+    }
+  }
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned long long *cnt =
+      p.counters + (size_t)((blockIdx.x * 4u + (threadIdx.x >> 5)) % VR_COUNTER_COPIES) * 8;
+  const unsigned vals[7] = {c.cTraces, c.cMiss, c.cGeo, c.cBnd, c.cRefl, c.cTerm, c.cScatter};
+  const int wordOf[7] = {1, 2, 3, 5, 6, 7, 4};
+#pragma unroll
+  for (int k = 0; k < (EXT ? 7 : 6); ++k) {
+    const unsigned v = __reduce_add_sync(0xffffffffu, vals[k]);
+    if (lane == 0 && v)
+      atomicAdd(&cnt[wordOf[k]], (unsigned long long)v);
+  }
+  if (p.work) {
+    const unsigned wv[5] = {wNodes, wPrims, c.wNb, c.wFlux, c.wSky};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const unsigned v = __reduce_add_sync(0xffffffffu, wv[k]);
+      if (lane == 0 && v)
+        atomicAdd(&p.work[k], (unsigned long long)v);
+    }
+  }
+}
+
+template <int EXT> static void launchTailExt(const TraceParams &p, unsigned grid, cudaStream_t s) {
+  if (p.scene.geoType == 0) {
+    if (p.scene.D == 2)
+      tailKernel<2, 0, EXT><<<grid, 128, 0, s>>>(p);
+    else
+      tailKernel<3, 0, EXT><<<grid, 128, 0, s>>>(p);
+  } else {
+    if (p.scene.D == 2)
+      tailKernel<2, 1, EXT><<<grid, 128, 0, s>>>(p);
+    else
+      tailKernel<3, 1, EXT><<<grid, 128, 0, s>>>(p);
+  }
+}
+
+cudaError_t launchTail(const TraceParams &p, cudaStream_t s) {
+  if (p.numSlots == 0)
+    return cudaSuccess;
+  const unsigned grid = (p.numSlots + 127u) / 128u;
+  if (p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST))
+    launchTailExt<1>(p, grid, s);
+  else
+    launchTailExt<0>(p, grid, s);
+  return cudaGetLastError();
 }
 
 // ctrl[0] slot cursor, ctrl[1] append cursor of the compacting mode, ctrl[2] slots in
