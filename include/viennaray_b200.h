@@ -196,8 +196,11 @@ int vr_debug_philox(vr_ctx *ctx, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t
 int vr_debug_reflect(vr_ctx *ctx, int kind, int D, const float *rayDir, const float *normal,
                      float coneMinAngle, uint32_t seed, uint64_t idx, uint32_t m, float *out3);
 /* acceleration-structure statistics: out[0] nodes, out[1] leaves, out[2]
- * max leaf size, out[3] node bytes, out[4] build ms (float bits) */
-int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out5);
+ * max leaf size, out[3] node bytes, out[4] build ms (float bits), out[5] / out[6]
+ * surface-area-heuristic terms (float bits): sum of the inner-node areas and of
+ * the leaf areas x primitive counts, over the root area, out[7] the Morton cell
+ * shape of the tree that was kept (float bits; 1 = like the scene box, 0 = cubic) */
+int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out8);
 /* per-phase device time: with timing enabled every kernel launch of vr_trace*
  * is bracketed by CUDA events on the context's stream; vr_debug_phase_ms
  * returns the milliseconds and launch counts accumulated since it was enabled

@@ -1,0 +1,23 @@
+"""CPU (-m "not gpu"): the reference arm of bench.py (the reference's own TraceKernel on host
+cores, or the oracle port when oracle/_ref is absent) prints the contract's JSON line."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "0", "--slices", "20", "--cpu-seconds", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "rays/s" and line["unit"] == "rays/s"
+    assert line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and line["gpu_launches"] == 0

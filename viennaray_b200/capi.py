@@ -325,11 +325,12 @@ class Context:
         return out
 
     def bvh_stats(self):
-        out = np.zeros(5, np.uint64)
+        out = np.zeros(8, np.uint64)
         self._ck(self.L.vr_debug_bvh_stats(self.h, _p(out)))
-        build_ms = np.array([out[4]], np.uint64).astype(np.uint32).view(np.float32)[0]
+        f = out[4:8].astype(np.uint32).view(np.float32)
         return {"nodes": int(out[0]), "leaves": int(out[1]), "max_leaf": int(out[2]),
-                "node_bytes": int(out[3]), "build_ms": float(build_ms)}
+                "node_bytes": int(out[3]), "build_ms": float(f[0]), "sah_inner": float(f[1]),
+                "sah_leaf": float(f[2]), "morton_alpha": float(f[3])}
 
     def phase_timing(self, enable):
         self._ck(self.L.vr_debug_phase_timing(self.h, 1 if enable else 0))

@@ -1187,6 +1187,12 @@ int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out5) {
   uint32_t bits;
   memcpy(&bits, &ctx->bvh.buildMs, 4);
   out5[4] = bits;
+  memcpy(&bits, &ctx->bvh.sahInner, 4);
+  out5[5] = bits;
+  memcpy(&bits, &ctx->bvh.sahLeaf, 4);
+  out5[6] = bits;
+  memcpy(&bits, &ctx->bvh.mortonAlpha, 4);
+  out5[7] = bits;
   return VR_OK;
 }
 

@@ -102,6 +102,9 @@ struct Bvh {
   float qLo[3] = {0, 0, 0}, qScale[3] = {1, 1, 1};
   float buildMs = 0.f;
   uint32_t numLeaves = 0, maxLeaf = 0;
+  float mortonAlpha = 1.f;  // shape of the Morton cells the kept tree was built with
+  float sahInner = 0.f, sahLeaf = 0.f;  // SAH terms: sum of inner-node areas, of leaf areas x
+                                        // primitive counts, both over the root area
 };
 cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, const float sceneLo[3],
                      const float sceneHi[3], cudaStream_t stream, Bvh *out);
