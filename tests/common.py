@@ -49,6 +49,13 @@ def case(name):
             scenes.hole_array(cells=2, pitch=40, radius=8, depth=48)
         return dict(name=name, D=3, geo="disk", points=p, normals=n, grid_delta=gd, bc=[0, 0, 0],
                     source_dir=host.POS_Z, kind=0, sticking=0.2, power=100.0, cone=0.0)
+    if name in ("sphere3D", "sphere2D"):  # tests/Resources/sphereGrid{3D,2D}_R1.dat (createRay etc.)
+        D = 3 if name == "sphere3D" else 2
+        return dict(name=name, D=D, geo="disk", points=I[name + "_points"],
+                    normals=I[name + "_normals"], grid_delta=float(I[name + "_gridDelta"]),
+                    bc=[0, 1, 0] if D == 3 else [1, 1, 1],
+                    source_dir=host.POS_Z if D == 3 else host.POS_Y, kind=2, sticking=0.3,
+                    power=4.0, cone=float(np.deg2rad(60.0)))
     if name == "plane":  # tests/rngSeed, tests/traceInterface geometry
         p, n = scenes.plane_grid(0.5, 5.0)
         return dict(name=name, D=3, geo="disk", points=p, normals=n, grid_delta=0.5, bc=[0, 0, 0],

@@ -80,7 +80,8 @@ def test_reflection_bit_exact(ctx0, kind, D):
     assert (o @ n > -1e-6).all()
 
 
-CASES = ["disk3D", "triangle3D", "disk2D", "trench", "trench_ion", "holes", "plane"]
+CASES = ["disk3D", "triangle3D", "disk2D", "trench", "trench_ion", "holes", "plane", "sphere3D",
+         "sphere2D"]
 
 
 @pytest.fixture(scope="module", params=CASES)
