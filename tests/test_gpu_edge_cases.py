@@ -133,3 +133,23 @@ def test_reuse_context_across_geometries():
         fo, _ = orc.trace(common.oracle_particle(c), orc.config(30000, SEED))
         assert (ctx.flux_download_fixed()[0] == fo).all(), name
     ctx.close()
+
+
+@pytest.mark.parametrize("shift", [(5000.0, -3000.0, 800.0), (-1.0e5, 2.0e5, -4.0e4)])
+def test_scene_far_from_the_origin(shift):
+    """coordinates that are large against the features: node quantisation, the boundary
+    pre-check margins and the sky map must stay conservative (results stay bit-equal)"""
+    c = common.case("trench")
+    c["points"] = (c["points"] + np.asarray(shift, np.float32)).astype(np.float32)
+    orc = common.make_oracle(c)
+    ctx, src, _ = common.make_gpu(c)
+    num = 80000
+    fo, io = orc.trace(common.oracle_particle(c), orc.config(num, SEED))
+    ctx.trace_device(src, [common.gpu_particle(c)], host.config(num, SEED), sync=True)
+    assert (ctx.flux_download_fixed()[0] == fo).all()
+    assert ctx.flux_download()[1][0].totalRaysTraced == io.totalTraces
+    rays = orc.source_rays(common.oracle_particle(c), orc.config(num, SEED), 0, 20000)
+    go, pr, to, _ = orc.intersect(rays)
+    gg, pg, tg, _, _ = ctx.debug_intersect(rays)
+    assert (go == gg).all() and (pr == pg).all()
+    ctx.close()
