@@ -11,7 +11,11 @@
 //                   regeneration of finished rays from the source
 //                   (rayTraceKernel.hpp:120-143).
 //
-// The host alternates the two until no slot is alive.  Results are identical
+//   tailKernel      once the source is dry and few rays survive: one thread per
+//                   ray runs traverse + shade in a loop to the ray's end, in one
+//                   launch (replaces ~1000 iterations of tiny launches).
+//
+// The host alternates the two until few slots are alive.  Results are identical
 // to running each ray to completion on its own (per-ray counter RNG, fixed
 // point flux sums), which is what the CPU oracle does.
 #include "vr_device.cuh"
