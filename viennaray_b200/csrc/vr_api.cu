@@ -624,6 +624,7 @@ int vr_scene_commit(vr_ctx *ctx) {
   s.nbOff = ctx->dNbOff;
   s.nbIdx = ctx->dNbIdx;
   s.nodes = ctx->bvh.nodes;
+  s.nodes4 = ctx->bvh.nodes4;
   s.rootRef = ctx->bvh.rootRef;
   s.sky = nullptr;  // rebuilt by the next trace
   ctx->committed = true;

@@ -221,6 +221,65 @@ __global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *s
     sah[2] = (double)area(nodeLo[0], nodeHi[0]);
 }
 
+// ---- optional 4-wide nodes (VR_BVH_WIDE=1): every live binary node collapses its two
+// children's children into one 64-byte node of up to four quantised boxes.  Entry k is
+// four words like a Node2 child; unused entries carry the reference VR_DONE.
+struct ChildBox {
+  float4 lo, hi;
+  uint32_t ref;
+};
+
+__device__ __forceinline__ ChildBox childOf(int i, int side, const float4 *lo, const float4 *hi,
+                                            const uint32_t *sorted, const int2 *range,
+                                            const int *split, const float4 *nodeLo,
+                                            const float4 *nodeHi) {
+  const int2 r = range[i];
+  const int c = split[i] + side;
+  const bool single = side == 0 ? (r.x == c) : (r.y == c);
+  ChildBox b;
+  if (single) {
+    const uint32_t p = sorted[c];
+    b.lo = lo[p];
+    b.hi = hi[p];
+    b.ref = VR_LEAF_FLAG | ((uint32_t)c << 4) | 1u;
+  } else {
+    b.lo = nodeLo[c];
+    b.hi = nodeHi[c];
+    const int2 rc = range[c];
+    b.ref = childRef(rc.x, rc.y, c);
+  }
+  return b;
+}
+
+__global__ void emit4Kernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
+                            const int2 *range, const int *split, const float4 *nodeLo,
+                            const float4 *nodeHi, uint4 *nodes4, float3 qLo, float3 qInv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+  const int2 r = range[i];
+  if ((uint32_t)(r.y - r.x + 1) <= VR_LEAF_MAX && i != 0)
+    return;
+  uint4 e[4];
+  int k = 0;
+  for (int side = 0; side < 2; ++side) {
+    const ChildBox b = childOf(i, side, lo, hi, sorted, range, split, nodeLo, nodeHi);
+    if (b.ref & VR_LEAF_FLAG) {
+      e[k++] = quantizeChild(b.lo, b.hi, qLo, qInv, b.ref);
+    } else {
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const ChildBox g =
+            childOf((int)b.ref, s2, lo, hi, sorted, range, split, nodeLo, nodeHi);
+        e[k++] = quantizeChild(g.lo, g.hi, qLo, qInv, g.ref);
+      }
+    }
+  }
+  for (; k < 4; ++k)
+    e[k] = make_uint4(0u, 0u, 0u, VR_DONE);
+  for (k = 0; k < 4; ++k)
+    nodes4[4 * (size_t)i + k] = e[k];
+}
+
 }  // namespace
 
 #define VR_CK(x)                                                                                   \
@@ -237,6 +296,7 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
                             const float sceneLo[3], const float sceneHi[3], float3 sInv,
                             cudaStream_t stream, Bvh *out) {
   freeBvh(out, stream);
+  const bool wide = getenv("VR_BVH_WIDE") && atoi(getenv("VR_BVH_WIDE")) > 0;
   unsigned long long *keys = nullptr, *keysSorted = nullptr;
   uint32_t *vals = nullptr;
   void *tmp = nullptr;
@@ -332,6 +392,13 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
                                                       range, split, nodeLo, nodeHi, out->nodes,
                                                       stats, qLo, qInv, sah);
     VR_CK(cudaGetLastError());
+    if (wide) {
+      VR_CK(cudaMallocAsync(&out->nodes4, sizeof(uint4) * 4 * (size_t)(n - 1), stream));
+      emit4Kernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(primLo, primHi, out->sortedToOrig, (int)n,
+                                                         range, split, nodeLo, nodeHi,
+                                                         out->nodes4, qLo, qInv);
+      VR_CK(cudaGetLastError());
+    }
     unsigned int hs[4];
     double hsah[4];
     VR_CK(cudaMemcpyAsync(hs, stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
@@ -418,6 +485,7 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
 
 void freeBvh(Bvh *b, cudaStream_t stream) {
   cudaFreeAsync(b->nodes, stream);
+  cudaFreeAsync(b->nodes4, stream);
   cudaFreeAsync(b->sortedToOrig, stream);
   *b = Bvh();
 }

@@ -10,6 +10,7 @@
 #ifndef VR_LEAF_MAX
 #define VR_LEAF_MAX 4u  // primitives per BVH leaf (<= 15)
 #endif
+#define VR_DONE 0x7fffffffu  // traversal finished / unused child (not a valid node index)
 #define VR_LEAF_FLAG 0x80000000u  // child reference: leaf(first << 4 | count)
 #define VR_FIXED_SCALE 1073741824.0f
 #define VR_COUNTER_COPIES 64      // replicated TraceInfo counters (summed on download)
@@ -36,6 +37,7 @@ struct DeviceScene {
   const uint32_t *nbOff;  // neighbour CSR, internal indices
   const uint32_t *nbIdx;
   const Node2 *nodes;
+  const uint4 *nodes4;  // optional 4-wide nodes or null
   uint32_t rootRef;
   float qLo[3], qScale[3];  // node box coordinate = qLo + q * qScale
   // sky map (vr_scene.cu buildSky): a G x G grid over the two lateral axes; per
@@ -96,6 +98,7 @@ struct TraceParams {
 // ---- acceleration structure (vr_bvh.cu) ----------------------------------
 struct Bvh {
   Node2 *nodes = nullptr;
+  uint4 *nodes4 = nullptr;  // optional 4-wide nodes (4 x uint4 each), same indices as `nodes`
   uint32_t numNodes = 0;
   uint32_t rootRef = 0;
   uint32_t *sortedToOrig = nullptr;  // device, numPrims

@@ -26,12 +26,14 @@ namespace vr {
 #ifndef VR_NODE_MIN
 #define VR_NODE_MIN 1  // lanes at inner nodes needed to keep the warp in the node loop
 #endif
-#define VR_DONE 0x7fffffffu  // traversal finished (not a valid node index)
 #ifndef VR_REFILL_MIN
 #define VR_REFILL_MIN 1  // idle lanes a warp waits for before it fetches new slots
 #endif
 #ifndef VR_TRAV_BLOCKS
 #define VR_TRAV_BLOCKS 12  // resident blocks per SM asked of ptxas (caps registers at 40)
+#endif
+#ifndef VR_TRAV_BLOCKS_WIDE
+#define VR_TRAV_BLOCKS_WIDE 12  // the same for the 4-wide node variant
 #endif
 #define VR_WDIST_CAP 64  // disks one ray can hit at once (hit disk + its neighbour list)
 #ifndef VR_SHADE_BLOCKS
@@ -235,8 +237,8 @@ __device__ __forceinline__ void traverseOne(const DeviceScene &sc, const V3 &org
 // ---------------------------------------------------------------------------
 // traverse: closest hit of every live slot
 // ---------------------------------------------------------------------------
-template <int GEO>
-__global__ void __launch_bounds__(128, VR_TRAV_BLOCKS) traverseKernel(const __grid_constant__ TraceParams p) {
+template <int GEO, int WIDE>
+__global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOCKS) traverseKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned ltMask = (1u << lane) - 1u;
@@ -319,7 +321,65 @@ __global__ void __launch_bounds__(128, VR_TRAV_BLOCKS) traverseKernel(const __gr
       if (!atNode)
         break;
 #endif
-      if (atNode) {
+      if (WIDE && atNode) {
+        // 4-wide node: four quantised boxes, hit children sorted near to far
+        uint4 c[4];
+        ldg256(sc.nodes4 + 4 * (size_t)cur, c[0], c[1]);
+        ldg256(sc.nodes4 + 4 * (size_t)cur + 2, c[2], c[3]);
+        ++wNodes;
+        float key[4];
+        uint32_t ref[4];
+        int count = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float t0x = __fmaf_rn((float)(c[k].x & 0xffffu), ix, ox),
+                      t1x = __fmaf_rn((float)(c[k].y >> 16), ix, ox);
+          const float t0y = __fmaf_rn((float)(c[k].x >> 16), iy, oy),
+                      t1y = __fmaf_rn((float)(c[k].z & 0xffffu), iy, oy);
+          const float t0z = __fmaf_rn((float)(c[k].y & 0xffffu), iz, oz),
+                      t1z = __fmaf_rn((float)(c[k].z >> 16), iz, oz);
+          const float nn =
+              fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
+          const float ff =
+              fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
+          const bool h = nn <= __fmaf_rn(ff, 1.00003f, 2e-6f) && c[k].w != VR_DONE;
+          key[k] = h ? nn : 3.402823466e+38f;
+          ref[k] = c[k].w;
+          count += h ? 1 : 0;
+        }
+#define VR_CSWAP(a, b)                                                                             \
+  {                                                                                                \
+    const bool s_ = key[b] < key[a];                                                               \
+    const float ka = s_ ? key[b] : key[a], kb = s_ ? key[a] : key[b];                              \
+    const uint32_t ra = s_ ? ref[b] : ref[a], rb = s_ ? ref[a] : ref[b];                           \
+    key[a] = ka;                                                                                   \
+    key[b] = kb;                                                                                   \
+    ref[a] = ra;                                                                                   \
+    ref[b] = rb;                                                                                   \
+  }
+        VR_CSWAP(0, 1)
+        VR_CSWAP(2, 3)
+        VR_CSWAP(0, 2)
+        VR_CSWAP(1, 3)
+        VR_CSWAP(1, 2)
+#undef VR_CSWAP
+        if (count == 0) {
+          cur = VR_DONE;
+          if (sp)
+            cur = stack[--sp];
+        } else {
+          cur = ref[0];
+          if (sp + 3 <= VR_STACK) {
+            if (count > 3)
+              stack[sp++] = ref[3];
+            if (count > 2)
+              stack[sp++] = ref[2];
+            if (count > 1)
+              stack[sp++] = ref[1];
+          }
+        }
+      }
+      if (!WIDE && atNode) {
         uint4 c0, c1;
         ldg256(sc.nodes + cur, c0, c1);
         ++wNodes;
@@ -404,30 +464,32 @@ __global__ void __launch_bounds__(128, VR_TRAV_BLOCKS) traverseKernel(const __gr
   }
 }
 
+template <int GEO, int WIDE>
+static cudaError_t launchTraverseT(const TraceParams &p, int numSMs, cudaStream_t s) {
+  static int perSM = 0;
+  if (perSM == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM,
+                                                                  traverseKernel<GEO, WIDE>, 128, 0);
+    if (e != cudaSuccess)
+      return e;
+    if (perSM < 1)
+      perSM = 1;
+  }
+  unsigned want = (p.numSlots + 127u) / 128u;
+  unsigned grid = (unsigned)(numSMs * perSM);
+  if (want < grid)
+    grid = want;
+  traverseKernel<GEO, WIDE><<<grid, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s) {
   if (p.numSlots == 0)
     return cudaSuccess;
-  static int perSM[2] = {0, 0};
-  const int g = p.scene.geoType ? 1 : 0;
-  if (perSM[g] == 0) {
-    cudaError_t e = g ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[g],
-                                                                     traverseKernel<1>, 128, 0)
-                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[g],
-                                                                     traverseKernel<0>, 128, 0);
-    if (e != cudaSuccess)
-      return e;
-    if (perSM[g] < 1)
-      perSM[g] = 1;
-  }
-  unsigned want = (p.numSlots + 127u) / 128u;
-  unsigned grid = (unsigned)(numSMs * perSM[g]);
-  if (want < grid)
-    grid = want;
-  if (g)
-    traverseKernel<1><<<grid, 128, 0, s>>>(p);
-  else
-    traverseKernel<0><<<grid, 128, 0, s>>>(p);
-  return cudaGetLastError();
+  const bool wide = p.scene.nodes4 != nullptr && p.scene.rootRef < VR_DONE;
+  if (p.scene.geoType)
+    return wide ? launchTraverseT<1, 1>(p, numSMs, s) : launchTraverseT<1, 0>(p, numSMs, s);
+  return wide ? launchTraverseT<0, 1>(p, numSMs, s) : launchTraverseT<0, 0>(p, numSMs, s);
 }
 
 // ---------------------------------------------------------------------------
