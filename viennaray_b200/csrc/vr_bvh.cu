@@ -153,7 +153,7 @@ __device__ __forceinline__ uint4 quantizeChild(float4 l, float4 h, float3 qLo, f
   };
   uint32_t lx = qdn(l.x, qLo.x, qInv.x), ly = qdn(l.y, qLo.y, qInv.y), lz = qdn(l.z, qLo.z, qInv.z);
   uint32_t hx = qup(h.x, qLo.x, qInv.x), hy = qup(h.y, qLo.y, qInv.y), hz = qup(h.z, qLo.z, qInv.z);
-  return make_uint4(lx | (ly << 16), lz | (hx << 16), hy | (hz << 16), ref);
+  return make_uint4(lx | (hx << 16), ly | (hy << 16), lz | (hz << 16), ref);
 }
 
 __global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,

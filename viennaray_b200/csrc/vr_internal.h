@@ -20,7 +20,7 @@ namespace vr {
 // Compressed binary BVH node, 32 bytes = one L2 sector: per child a box of six
 // 16-bit coordinates on the scene's quantisation grid (rounded outwards) and a
 // 32-bit reference.
-//   c.x = lo.x | lo.y << 16   c.y = lo.z | hi.x << 16   c.z = hi.y | hi.z << 16
+//   c.x = lo.x | hi.x << 16   c.y = lo.y | hi.y << 16   c.z = lo.z | hi.z << 16
 //   c.w = reference (inner node index, or VR_LEAF_FLAG | first << 4 | count)
 struct alignas(16) Node2 {
   uint4 c0, c1;

@@ -30,10 +30,10 @@ namespace vr {
 #define VR_REFILL_MIN 1  // idle lanes a warp waits for before it fetches new slots
 #endif
 #ifndef VR_TRAV_BLOCKS
-#define VR_TRAV_BLOCKS 12  // resident blocks per SM asked of ptxas (caps registers at 40)
+#define VR_TRAV_BLOCKS 10  // resident blocks per SM asked of ptxas (caps registers at 48)
 #endif
 #ifndef VR_TRAV_BLOCKS_WIDE
-#define VR_TRAV_BLOCKS_WIDE 12  // the same for the 4-wide node variant
+#define VR_TRAV_BLOCKS_WIDE 10  // the same for the 4-wide node variant
 #endif
 #define VR_WDIST_CAP 64  // disks one ray can hit at once (hit disk + its neighbour list)
 #ifndef VR_SHADE_BLOCKS
@@ -152,6 +152,53 @@ __device__ __forceinline__ unsigned long long warpSum(unsigned long long v) {
   return v;
 }
 
+// Slab test of one quantised child box.  A node word holds the low and the high plane
+// of one axis (16 bits each); sel* is the byte-permute selector that picks the plane the
+// ray enters through (0x7610: low half, 0x7632: high half, by the sign of the slope) and
+// sel ^ 0x22 the one it leaves through.  The permute also supplies the exponent 0x4B00,
+// so the word read as a float is 2^23 + q and the conversion costs no instruction of its
+// own: t = (2^23 + q) * slope + (offset - 2^23 * slope).  The folded offset is rounded at
+// the magnitude 2^23 * slope, i.e. to half a grid cell; the boxes were widened by a full
+// cell at build time, so the test stays conservative.
+struct NodeRay {
+  float ix, iy, iz, ox, oy, oz;
+  uint32_t sx, sy, sz;
+};
+__device__ __forceinline__ NodeRay makeNodeRay(const DeviceScene &sc, const V3 &org, const V3 &dir) {
+  NodeRay r;
+  // reciprocal for the slab tests only; a zero component becomes a huge finite slope so
+  // that lo*ix - org*ix keeps the right sign
+  r.ix = 1.f / (fabsf(dir.x) > 1e-20f ? dir.x : copysignf(1e-20f, dir.x));
+  r.iy = 1.f / (fabsf(dir.y) > 1e-20f ? dir.y : copysignf(1e-20f, dir.y));
+  r.iz = 1.f / (fabsf(dir.z) > 1e-20f ? dir.z : copysignf(1e-20f, dir.z));
+  // node boxes live on the 16-bit grid: t = q * (scale/d) + (qLo - org)/d
+  r.ox = (sc.qLo[0] - org.x) * r.ix;
+  r.oy = (sc.qLo[1] - org.y) * r.iy;
+  r.oz = (sc.qLo[2] - org.z) * r.iz;
+  r.ix *= sc.qScale[0];
+  r.iy *= sc.qScale[1];
+  r.iz *= sc.qScale[2];
+  r.ox = __fmaf_rn(-8388608.f, r.ix, r.ox);
+  r.oy = __fmaf_rn(-8388608.f, r.iy, r.oy);
+  r.oz = __fmaf_rn(-8388608.f, r.iz, r.oz);
+  r.sx = r.ix < 0.f ? 0x7632u : 0x7610u;
+  r.sy = r.iy < 0.f ? 0x7632u : 0x7610u;
+  r.sz = r.iz < 0.f ? 0x7632u : 0x7610u;
+  return r;
+}
+__device__ __forceinline__ void slabChild(const uint4 c, const NodeRay &r, float tmax, float &n,
+                                          float &f) {
+  const uint32_t M = 0x4B000000u;
+  const float nx = __fmaf_rn(__uint_as_float(__byte_perm(c.x, M, r.sx)), r.ix, r.ox);
+  const float fx = __fmaf_rn(__uint_as_float(__byte_perm(c.x, M, r.sx ^ 0x22u)), r.ix, r.ox);
+  const float ny = __fmaf_rn(__uint_as_float(__byte_perm(c.y, M, r.sy)), r.iy, r.oy);
+  const float fy = __fmaf_rn(__uint_as_float(__byte_perm(c.y, M, r.sy ^ 0x22u)), r.iy, r.oy);
+  const float nz = __fmaf_rn(__uint_as_float(__byte_perm(c.z, M, r.sz)), r.iz, r.oz);
+  const float fz = __fmaf_rn(__uint_as_float(__byte_perm(c.z, M, r.sz ^ 0x22u)), r.iz, r.oz);
+  n = fmaxf(fmaxf(nx, ny), fmaxf(nz, VR_TNEAR));
+  f = fminf(fminf(fx, fy), fminf(fz, tmax));
+}
+
 // ---------------------------------------------------------------------------
 // closest hit of ONE ray by its own thread (no warp cooperation): the tail
 // kernel's traversal.  Same node / primitive tests as traverseKernel; `best`
@@ -162,14 +209,7 @@ __device__ __forceinline__ void traverseOne(const DeviceScene &sc, const V3 &org
                                             Hit &best, unsigned &wNodes, unsigned &wPrims) {
   if (!sc.numPrims)
     return;
-  float ix = 1.f / (fabsf(dir.x) > 1e-20f ? dir.x : copysignf(1e-20f, dir.x));
-  float iy = 1.f / (fabsf(dir.y) > 1e-20f ? dir.y : copysignf(1e-20f, dir.y));
-  float iz = 1.f / (fabsf(dir.z) > 1e-20f ? dir.z : copysignf(1e-20f, dir.z));
-  const float ox = (sc.qLo[0] - org.x) * ix, oy = (sc.qLo[1] - org.y) * iy,
-              oz = (sc.qLo[2] - org.z) * iz;
-  ix *= sc.qScale[0];
-  iy *= sc.qScale[1];
-  iz *= sc.qScale[2];
+  const NodeRay nr = makeNodeRay(sc, org, dir);
   uint32_t stack[VR_STACK];
   int sp = 0;
   uint32_t cur = sc.rootRef;
@@ -178,26 +218,9 @@ __device__ __forceinline__ void traverseOne(const DeviceScene &sc, const V3 &org
       uint4 c0, c1;
       ldg256(sc.nodes + cur, c0, c1);
       ++wNodes;
-      const float t0x = __fmaf_rn((float)(c0.x & 0xffffu), ix, ox),
-                  t1x = __fmaf_rn((float)(c0.y >> 16), ix, ox);
-      const float t0y = __fmaf_rn((float)(c0.x >> 16), iy, oy),
-                  t1y = __fmaf_rn((float)(c0.z & 0xffffu), iy, oy);
-      const float t0z = __fmaf_rn((float)(c0.y & 0xffffu), iz, oz),
-                  t1z = __fmaf_rn((float)(c0.z >> 16), iz, oz);
-      const float n0 =
-          fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
-      const float f0 =
-          fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
-      const float u0x = __fmaf_rn((float)(c1.x & 0xffffu), ix, ox),
-                  u1x = __fmaf_rn((float)(c1.y >> 16), ix, ox);
-      const float u0y = __fmaf_rn((float)(c1.x >> 16), iy, oy),
-                  u1y = __fmaf_rn((float)(c1.z & 0xffffu), iy, oy);
-      const float u0z = __fmaf_rn((float)(c1.y & 0xffffu), iz, oz),
-                  u1z = __fmaf_rn((float)(c1.z >> 16), iz, oz);
-      const float n1 =
-          fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), VR_TNEAR));
-      const float f1 =
-          fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), best.t));
+      float n0, f0, n1, f1;
+      slabChild(c0, nr, best.t, n0, f0);
+      slabChild(c1, nr, best.t, n1, f1);
       const bool h0 = n0 * 0.99999f <= f0 * 1.00001f + 1e-6f;
       const bool h1 = n1 * 0.99999f <= f1 * 1.00001f + 1e-6f;
       const uint32_t r0 = c0.w, r1 = c1.w;
@@ -246,7 +269,7 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
 
   uint32_t slot = VR_INVALID_ID;
   V3 org = {0.f, 0.f, 0.f}, dir = {0.f, 0.f, 1.f};
-  float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+  NodeRay nr = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0x7610u, 0x7610u, 0x7610u};
   Hit best;
   best.t = 0.f;
   best.geom = best.prim = best.orig = VR_INVALID_ID;
@@ -277,18 +300,7 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
             slot = s;
             org = {a.x, a.y, a.z};
             dir = {a.w, b.x, b.y};
-            // reciprocal for the slab tests only; a zero component becomes a
-            // huge finite slope so that lo*ix - org*ix keeps the right sign
-            ix = 1.f / (fabsf(dir.x) > 1e-20f ? dir.x : copysignf(1e-20f, dir.x));
-            iy = 1.f / (fabsf(dir.y) > 1e-20f ? dir.y : copysignf(1e-20f, dir.y));
-            iz = 1.f / (fabsf(dir.z) > 1e-20f ? dir.z : copysignf(1e-20f, dir.z));
-            // node boxes live on the 16-bit grid: t = q * (scale/d) + (qLo - org)/d
-            ox = (sc.qLo[0] - org.x) * ix;
-            oy = (sc.qLo[1] - org.y) * iy;
-            oz = (sc.qLo[2] - org.z) * iz;
-            ix *= sc.qScale[0];
-            iy *= sc.qScale[1];
-            iz *= sc.qScale[2];
+            nr = makeNodeRay(sc, org, dir);
             // the shade / init kernel already intersected the boundary box
             const float4 h0 = __ldcs(&p.pool.hit[s]);
             best.t = h0.x;
@@ -332,16 +344,8 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
         int count = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float t0x = __fmaf_rn((float)(c[k].x & 0xffffu), ix, ox),
-                      t1x = __fmaf_rn((float)(c[k].y >> 16), ix, ox);
-          const float t0y = __fmaf_rn((float)(c[k].x >> 16), iy, oy),
-                      t1y = __fmaf_rn((float)(c[k].z & 0xffffu), iy, oy);
-          const float t0z = __fmaf_rn((float)(c[k].y & 0xffffu), iz, oz),
-                      t1z = __fmaf_rn((float)(c[k].z >> 16), iz, oz);
-          const float nn =
-              fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
-          const float ff =
-              fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
+          float nn, ff;
+          slabChild(c[k], nr, best.t, nn, ff);
           const bool h = nn <= __fmaf_rn(ff, 1.00003f, 2e-6f) && c[k].w != VR_DONE;
           key[k] = h ? nn : 3.402823466e+38f;
           ref[k] = c[k].w;
@@ -383,29 +387,12 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
         uint4 c0, c1;
         ldg256(sc.nodes + cur, c0, c1);
         ++wNodes;
-        // slab tests with an explicit FMA per plane; the boxes were rounded
-        // outwards by a full grid cell at build time and the comparison is
+        // slab tests with an explicit FMA per plane (slabChild); the boxes were
+        // rounded outwards by a full grid cell at build time and the comparison is
         // widened, so rounding here can only add visits
-        const float t0x = __fmaf_rn((float)(c0.x & 0xffffu), ix, ox),
-                    t1x = __fmaf_rn((float)(c0.y >> 16), ix, ox);
-        const float t0y = __fmaf_rn((float)(c0.x >> 16), iy, oy),
-                    t1y = __fmaf_rn((float)(c0.z & 0xffffu), iy, oy);
-        const float t0z = __fmaf_rn((float)(c0.y & 0xffffu), iz, oz),
-                    t1z = __fmaf_rn((float)(c0.z >> 16), iz, oz);
-        const float n0 =
-            fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), VR_TNEAR));
-        const float f0 =
-            fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
-        const float u0x = __fmaf_rn((float)(c1.x & 0xffffu), ix, ox),
-                    u1x = __fmaf_rn((float)(c1.y >> 16), ix, ox);
-        const float u0y = __fmaf_rn((float)(c1.x >> 16), iy, oy),
-                    u1y = __fmaf_rn((float)(c1.z & 0xffffu), iy, oy);
-        const float u0z = __fmaf_rn((float)(c1.y & 0xffffu), iz, oz),
-                    u1z = __fmaf_rn((float)(c1.z >> 16), iz, oz);
-        const float n1 =
-            fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), VR_TNEAR));
-        const float f1 =
-            fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), best.t));
+        float n0, f0, n1, f1;
+        slabChild(c0, nr, best.t, n0, f0);
+        slabChild(c1, nr, best.t, n1, f1);
         const bool h0 = n0 <= __fmaf_rn(f0, 1.00003f, 2e-6f);
         const bool h1 = n1 <= __fmaf_rn(f1, 1.00003f, 2e-6f);
         const uint32_t r0 = c0.w, r1 = c1.w;
