@@ -241,14 +241,11 @@ struct Hit {
   uint32_t prim;  // internal index for geometry, 0..7 for the boundary
   uint32_t orig;  // original primitive ID (tie-break key)
 };
+// smallest t, then lower geomID, then lower original primID; written without branches
+// (t and b.t are never NaN here) because only a few lanes of a warp ever get this far
 __device__ __forceinline__ bool better(float t, uint32_t geom, uint32_t orig, const Hit &b) {
-  if (t < b.t)
-    return true;
-  if (t > b.t)
-    return false;
-  if (geom != b.geom)
-    return geom < b.geom;
-  return orig < b.orig;
+  const bool tie = (geom < b.geom) | ((geom == b.geom) & (orig < b.orig));
+  return (t < b.t) | ((t == b.t) & tie);
 }
 
 // oriented disc: den = dot(dir,n); t = dot(c-org,n)/den; tnear <= t;
@@ -258,7 +255,13 @@ __device__ __forceinline__ void testDisk(const float4 P, const float4 N, uint32_
   float den = dot3(dir.x, dir.y, dir.z, N.x, N.y, N.z);
   if (den == 0.f)
     return;
-  float t = dot3(P.x - org.x, P.y - org.y, P.z - org.z, N.x, N.y, N.z) / den;
+  // a ray that starts in the disk's own plane (every reflection off a flat region meets
+  // its coplanar neighbours like this) has num == 0 exactly: t = +-0 fails the tnear test
+  // either way, and returning here keeps the warp out of the division's slow path
+  const float num = dot3(P.x - org.x, P.y - org.y, P.z - org.z, N.x, N.y, N.z);
+  if (num == 0.f)
+    return;
+  float t = num / den;
   if (!(VR_TNEAR <= t && t <= 3.402823466e+38f))
     return;
   float qx = (org.x + dir.x * t) - P.x, qy = (org.y + dir.y * t) - P.y,

@@ -68,9 +68,12 @@ __device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, co
     const float c = sc.bbox[k & 1][axis];
     const float da = comp(dir, axis);
     tpk[k] = 3.402823466e+38f;
-    if (da == 0.f)
+    // (a ray that starts on the plane has a zero numerator: tp = 0 is rejected below
+    // anyway, and skipping it here avoids the division's slow path)
+    const float nb = c - comp(org, axis);
+    if (da == 0.f || nb == 0.f)
       continue;
-    const float tp = (c - comp(org, axis)) / da;
+    const float tp = nb / da;
     if (!(tp >= 0.5f * VR_TNEAR && tp <= best.t * 1.00001f + 1e-5f))
       continue;
     // the plane's two triangles tile the box face: skip them when the plane
