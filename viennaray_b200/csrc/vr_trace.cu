@@ -171,9 +171,10 @@ __device__ __forceinline__ NodeRay makeNodeRay(const DeviceScene &sc, const V3 &
   NodeRay r;
   // reciprocal for the slab tests only; a zero component becomes a huge finite slope so
   // that lo*ix - org*ix keeps the right sign
-  r.ix = 1.f / (fabsf(dir.x) > 1e-20f ? dir.x : copysignf(1e-20f, dir.x));
-  r.iy = 1.f / (fabsf(dir.y) > 1e-20f ? dir.y : copysignf(1e-20f, dir.y));
-  r.iz = 1.f / (fabsf(dir.z) > 1e-20f ? dir.z : copysignf(1e-20f, dir.z));
+  // (approximate reciprocal: the slope only steers the conservative box tests)
+  r.ix = __fdividef(1.f, fabsf(dir.x) > 1e-20f ? dir.x : copysignf(1e-20f, dir.x));
+  r.iy = __fdividef(1.f, fabsf(dir.y) > 1e-20f ? dir.y : copysignf(1e-20f, dir.y));
+  r.iz = __fdividef(1.f, fabsf(dir.z) > 1e-20f ? dir.z : copysignf(1e-20f, dir.z));
   // node boxes live on the 16-bit grid: t = q * (scale/d) + (qLo - org)/d
   r.ox = (sc.qLo[0] - org.x) * r.ix;
   r.oy = (sc.qLo[1] - org.y) * r.iy;
@@ -263,7 +264,7 @@ __device__ __forceinline__ void traverseOne(const DeviceScene &sc, const V3 &org
 // ---------------------------------------------------------------------------
 // traverse: closest hit of every live slot
 // ---------------------------------------------------------------------------
-template <int GEO, int WIDE>
+template <int GEO, int WIDE, int COUNT>
 __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOCKS) traverseKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const unsigned lane = threadIdx.x & 31u;
@@ -341,7 +342,8 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
         uint4 c[4];
         ldg256(sc.nodes4 + 4 * (size_t)cur, c[0], c[1]);
         ldg256(sc.nodes4 + 4 * (size_t)cur + 2, c[2], c[3]);
-        ++wNodes;
+        if (COUNT)
+          ++wNodes;
         float key[4];
         uint32_t ref[4];
         int count = 0;
@@ -389,7 +391,8 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
       if (!WIDE && atNode) {
         uint4 c0, c1;
         ldg256(sc.nodes + cur, c0, c1);
-        ++wNodes;
+        if (COUNT)
+          ++wNodes;
         // slab tests with an explicit FMA per plane (slabChild); the boxes were
         // rounded outwards by a full grid cell at build time and the comparison is
         // widened, so rounding here can only add visits
@@ -433,7 +436,8 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
                   org, dir, best, nullptr);
         }
       }
-      wPrims += count;
+      if (COUNT)
+        wPrims += count;
     }
 
     // ---- finished: publish the hit, free the lane ---------------------------------
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
     }
   }
 
-  if (p.work) {
+  if (COUNT && p.work) {
     unsigned long long a = warpSum((unsigned long long)wNodes),
                        b = warpSum((unsigned long long)wPrims);
     if (lane == 0) {
@@ -454,12 +458,12 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
   }
 }
 
-template <int GEO, int WIDE>
+template <int GEO, int WIDE, int COUNT>
 static cudaError_t launchTraverseT(const TraceParams &p, int numSMs, cudaStream_t s) {
   static int perSM = 0;
   if (perSM == 0) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM,
-                                                                  traverseKernel<GEO, WIDE>, 128, 0);
+                                                                  traverseKernel<GEO, WIDE, COUNT>, 128, 0);
     if (e != cudaSuccess)
       return e;
     if (perSM < 1)
@@ -469,7 +473,7 @@ static cudaError_t launchTraverseT(const TraceParams &p, int numSMs, cudaStream_
   unsigned grid = (unsigned)(numSMs * perSM);
   if (want < grid)
     grid = want;
-  traverseKernel<GEO, WIDE><<<grid, 128, 0, s>>>(p);
+  traverseKernel<GEO, WIDE, COUNT><<<grid, 128, 0, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -477,9 +481,18 @@ cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s) {
   if (p.numSlots == 0)
     return cudaSuccess;
   const bool wide = p.scene.nodes4 != nullptr && p.scene.rootRef < VR_DONE;
-  if (p.scene.geoType)
-    return wide ? launchTraverseT<1, 1>(p, numSMs, s) : launchTraverseT<1, 0>(p, numSMs, s);
-  return wide ? launchTraverseT<0, 1>(p, numSMs, s) : launchTraverseT<0, 0>(p, numSMs, s);
+  // the work counters (VR_COUNT_WORK) are compiled out of the normal kernels
+  const int which = (p.scene.geoType ? 4 : 0) | (wide ? 2 : 0) | (p.work ? 1 : 0);
+  switch (which) {
+  case 0: return launchTraverseT<0, 0, 0>(p, numSMs, s);
+  case 1: return launchTraverseT<0, 0, 1>(p, numSMs, s);
+  case 2: return launchTraverseT<0, 1, 0>(p, numSMs, s);
+  case 3: return launchTraverseT<0, 1, 1>(p, numSMs, s);
+  case 4: return launchTraverseT<1, 0, 0>(p, numSMs, s);
+  case 5: return launchTraverseT<1, 0, 1>(p, numSMs, s);
+  case 6: return launchTraverseT<1, 1, 0>(p, numSMs, s);
+  default: return launchTraverseT<1, 1, 1>(p, numSMs, s);
+  }
 }
 
 // ---------------------------------------------------------------------------
