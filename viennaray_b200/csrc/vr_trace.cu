@@ -59,33 +59,38 @@ __device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, co
   const float ext = fmaxf(fmaxf(sc.bbox[1][0] - sc.bbox[0][0], sc.bbox[1][1] - sc.bbox[0][1]),
                           sc.bbox[1][2] - sc.bbox[0][2]);
   // 1. all lanes together: which of the four planes can the ray hit inside the
-  //    box face?  (usually one.)  Their plane distances select the order.
+  //    box face?  (usually one.)  Their plane distances select the order.  This is a
+  //    pre-check with margins, so the plane distance comes from an approximate
+  //    reciprocal; planes 0,1 bound the first lateral axis, planes 2,3 the second.
   float tpk[4];
   unsigned cand = 0u;
+  const int a0 = sc.firstDir, a1 = sc.secondDir, a2 = 3 - a0 - a1;
+  const float o[3] = {comp(org, a0), comp(org, a1), comp(org, a2)};
+  const float d[3] = {comp(dir, a0), comp(dir, a1), comp(dir, a2)};
+  const float lo[3] = {sc.bbox[0][a0], sc.bbox[0][a1], sc.bbox[0][a2]};
+  const float hi[3] = {sc.bbox[1][a0], sc.bbox[1][a1], sc.bbox[1][a2]};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int axis = k < 2 ? sc.firstDir : sc.secondDir;
-    const float c = sc.bbox[k & 1][axis];
-    const float da = comp(dir, axis);
-    tpk[k] = 3.402823466e+38f;
-    // (a ray that starts on the plane has a zero numerator: tp = 0 is rejected below
-    // anyway, and skipping it here avoids the division's slow path)
-    const float nb = c - comp(org, axis);
-    if (da == 0.f || nb == 0.f)
+  for (int e = 0; e < 2; ++e) {  // e: the plane's axis, f: the other lateral axis
+    const int f = 1 - e;
+    tpk[2 * e] = tpk[2 * e + 1] = 3.402823466e+38f;
+    if (d[e] == 0.f)
       continue;
-    const float tp = nb / da;
-    if (!(tp >= 0.5f * VR_TNEAR && tp <= best.t * 1.00001f + 1e-5f))
-      continue;
-    // the plane's two triangles tile the box face: skip them when the plane
-    // point is clearly outside that rectangle
-    const float m = 1e-4f * (ext + fabsf(tp));
-    const float hx = org.x + dir.x * tp, hy = org.y + dir.y * tp, hz = org.z + dir.z * tp;
-    if ((axis != 0 && (hx < sc.bbox[0][0] - m || hx > sc.bbox[1][0] + m)) ||
-        (axis != 1 && (hy < sc.bbox[0][1] - m || hy > sc.bbox[1][1] + m)) ||
-        (axis != 2 && (hz < sc.bbox[0][2] - m || hz > sc.bbox[1][2] + m)))
-      continue;
-    tpk[k] = tp;
-    cand |= 1u << k;
+    const float rd = __fdividef(1.f, d[e]);
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      // (a ray that starts on the plane has a zero numerator and is skipped)
+      const float tp = ((side ? hi[e] : lo[e]) - o[e]) * rd;
+      if (!(tp >= 0.5f * VR_TNEAR && tp <= 3.402823466e+38f))
+        continue;
+      // the plane's two triangles tile the box face: skip them when the plane
+      // point is clearly outside that rectangle
+      const float m = 1e-4f * (ext + fabsf(tp));
+      const float hf = o[f] + d[f] * tp, hu = o[2] + d[2] * tp;
+      if (hf < lo[f] - m || hf > hi[f] + m || hu < lo[2] - m || hu > hi[2] + m)
+        continue;
+      tpk[2 * e + side] = tp;
+      cand |= 1u << (2 * e + side);
+    }
   }
   // 2. the exact triangle tests, nearest candidate plane first; the lanes of a warp run
   //    this loop side by side on their own planes instead of idling through a loop over
