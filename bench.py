@@ -342,7 +342,7 @@ def main():
                         "host buffers"},
         "gpu_launches": launches,
         "roofline": {
-            "kernel": "traverseKernel<0>", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "kernel": "traverseKernel<0,0,0>", "bound": "hbm", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak,
             # DRAM bytes of an average launch: ncu's dram__bytes_{read,write}.sum per traversed
             # slot (one --set full capture, profiles/traffic.json) x traversals per launch

@@ -156,11 +156,13 @@ __device__ __forceinline__ uint4 quantizeChild(float4 l, float4 h, float3 qLo, f
   return make_uint4(lx | (hx << 16), ly | (hy << 16), lz | (hz << 16), ref);
 }
 
-__global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
-                           const int2 *range, const int *split, const float4 *nodeLo,
-                           const float4 *nodeHi, Node2 *nodes, unsigned int *stats, float3 qLo,
-                           float3 qInv, double *sah) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void emitNode(int i, const float4 *lo, const float4 *hi,
+                                         const uint32_t *sorted, int n, const int2 *range,
+                                         const int *split, const float4 *nodeLo,
+                                         const float4 *nodeHi, Node2 *nodes, float3 qLo,
+                                         float3 qInv, double *sah, double &aIn, double &aLeaf,
+                                         unsigned &cNodes, unsigned &cLeaves,
+                                         unsigned &cMaxLeaf) {
   if (i >= n - 1)
     return;
   int2 r = range[i];
@@ -195,14 +197,12 @@ __global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *s
   nd.c0 = quantizeChild(l0, h0, qLo, qInv, ref0);
   nd.c1 = quantizeChild(l1, h1, qLo, qInv, ref1);
   nodes[i] = nd;
-  atomicAdd(&stats[0], 1u);
-  unsigned leaves = ((ref0 & VR_LEAF_FLAG) ? 1u : 0u) + ((ref1 & VR_LEAF_FLAG) ? 1u : 0u);
-  if (leaves)
-    atomicAdd(&stats[1], leaves);
+  cNodes = 1u;
+  cLeaves = ((ref0 & VR_LEAF_FLAG) ? 1u : 0u) + ((ref1 & VR_LEAF_FLAG) ? 1u : 0u);
   if (ref0 & VR_LEAF_FLAG)
-    atomicMax(&stats[2], ref0 & 15u);
+    cMaxLeaf = ref0 & 15u;
   if (ref1 & VR_LEAF_FLAG)
-    atomicMax(&stats[2], ref1 & 15u);
+    cMaxLeaf = max(cMaxLeaf, ref1 & 15u);
   // surface-area-heuristic terms: area of this inner node, areas of its leaf children
   // times their primitive counts (the host divides by the root area)
   auto area = [](float4 l, float4 h) {
@@ -214,11 +214,40 @@ __global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *s
     leafArea += area(l0, h0) * (float)(ref0 & 15u);
   if (ref1 & VR_LEAF_FLAG)
     leafArea += area(l1, h1) * (float)(ref1 & 15u);
-  atomicAdd(&sah[0], (double)area(nodeLo[i], nodeHi[i]));
-  if (leafArea > 0.f)
-    atomicAdd(&sah[1], (double)leafArea);
+  aIn = (double)area(nodeLo[i], nodeHi[i]);
+  aLeaf = (double)leafArea;
   if (i == 0)
-    sah[2] = (double)area(nodeLo[0], nodeHi[0]);
+    sah[2] = aIn;
+}
+
+__global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
+                           const int2 *range, const int *split, const float4 *nodeLo,
+                           const float4 *nodeHi, Node2 *nodes, unsigned int *stats, float3 qLo,
+                           float3 qInv, double *sah) {
+  double aIn = 0., aLeaf = 0.;
+  unsigned cNodes = 0u, cLeaves = 0u, cMaxLeaf = 0u;
+  emitNode(blockIdx.x * blockDim.x + threadIdx.x, lo, hi, sorted, n, range, split, nodeLo, nodeHi,
+           nodes, qLo, qInv, sah, aIn, aLeaf, cNodes, cLeaves, cMaxLeaf);
+  // statistics and SAH terms summed per warp first: a million atomics on one address
+  // serialise
+  cNodes = __reduce_add_sync(0xffffffffu, cNodes);
+  cLeaves = __reduce_add_sync(0xffffffffu, cLeaves);
+  cMaxLeaf = __reduce_max_sync(0xffffffffu, cMaxLeaf);
+  for (int o = 16; o > 0; o >>= 1) {
+    aIn += __shfl_down_sync(0xffffffffu, aIn, o);
+    aLeaf += __shfl_down_sync(0xffffffffu, aLeaf, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cNodes) {
+      atomicAdd(&stats[0], cNodes);
+      atomicAdd(&stats[1], cLeaves);
+      atomicMax(&stats[2], cMaxLeaf);
+    }
+    if (aIn > 0.)
+      atomicAdd(&sah[0], aIn);
+    if (aLeaf > 0.)
+      atomicAdd(&sah[1], aLeaf);
+  }
 }
 
 // ---- optional 4-wide nodes (VR_BVH_WIDE=1): every live binary node collapses its two
