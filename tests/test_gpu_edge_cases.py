@@ -153,3 +153,27 @@ def test_scene_far_from_the_origin(shift):
     gg, pg, tg, _, _ = ctx.debug_intersect(rays)
     assert (go == gg).all() and (pr == pg).all()
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["trench", "triangle3D"])
+@pytest.mark.parametrize("n", [0, 3, 5, 9])
+def test_wide_nodes_option(monkeypatch, name, n):
+    """VR_BVH_WIDE=1 (4-wide nodes, read when the scene is committed) changes the order of the
+    traversal only: IDs, t and the whole-walk flux words stay those of the oracle.  n > 0:
+    tiny scenes whose wide root has unused entries."""
+    monkeypatch.setenv("VR_BVH_WIDE", "1")
+    c = tiny_case(n) if n else common.case(name)
+    if n and name != "trench":
+        pytest.skip("tiny scenes are disk scenes")
+    orc = common.make_oracle(c)
+    ctx, src, _ = common.make_gpu(c)
+    rays = 20000 if n else 200000
+    fo, io = orc.trace(common.oracle_particle(c), orc.config(rays, SEED))
+    ctx.trace_device(src, [common.gpu_particle(c)], host.config(rays, SEED), sync=True)
+    assert (ctx.flux_download_fixed()[0] == fo).all()
+    assert ctx.flux_download()[1][0].totalRaysTraced == io.totalTraces
+    probe = orc.source_rays(common.oracle_particle(c), orc.config(4000, SEED), 0, 4000)
+    go, pr, to, _ = orc.intersect(probe)
+    gg, pg, tg, _, _ = ctx.debug_intersect(probe)
+    assert (go == gg).all() and (pr == pg).all() and (to == tg).all()
+    ctx.close()
