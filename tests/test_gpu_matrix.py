@@ -46,8 +46,10 @@ def run_pair(c, num, max_refl=0xFFFFFFFF, max_bhits=1000, primary_dir=None, mfp=
                                  wdist=wdist), sync=True)
     fg = ctx.flux_download_fixed()[0]
     ig = ctx.flux_download()[1][0]
+    launches = ctx.last_launch_count()
     ctx.close()
     d = io.as_dict()
+    d["launches"], d["iterations"] = launches
     assert (fg == fo).all(), "%d primitives differ" % int((fg != fo).sum())
     assert (ig.totalRaysTraced, ig.geometryHits, ig.nonGeometryHits, ig.boundaryHits,
             ig.reflections, ig.raysTerminated, ig.particleHits) == \
@@ -139,3 +141,32 @@ def test_distance_weighted_spread(name, pname):
     run_pair(c, 60000, wdist=True)
     # and both options together
     run_pair(c, 30000, wdist=True, mfp=10.0)
+
+
+@pytest.mark.parametrize("name", ["trench", "trench_ion", "triangle3D", "sphere2D"])
+@pytest.mark.parametrize("pool,tail", [(4096, 0), (4096, 262144), (1 << 16, 0), (0, 0)])
+def test_wavefront_schedule_does_not_change_results(monkeypatch, name, pool, tail):
+    """The small cases above end up in the single-launch tail kernel almost at once.  Here
+    the schedule is forced the other ways (both read at vr_ctx_create): a pool far smaller
+    than the job, so that slots are regenerated in place over many wavefront iterations
+    before the source runs dry, and VR_TAIL_RAYS=0, so that the traverse / shade / flip
+    kernels -- not the tail kernel -- carry every ray to its end.  Flux words and counters
+    must still be the oracle's."""
+    if pool:
+        monkeypatch.setenv("VR_POOL_SLOTS", str(pool))
+    monkeypatch.setenv("VR_TAIL_RAYS", str(tail))
+    c = common.case(name)
+    d = run_pair(c, 150000)
+    if pool == 4096:  # at least one wavefront iteration per pool refill
+        assert d["iterations"] >= 150000 // 4096
+    if tail == 0:  # and the walk's long tail is made of iterations, not of one tail launch
+        assert d["iterations"] >= 20
+
+
+@pytest.mark.parametrize("mfp,wdist", [(3.0, False), (0.0, True)])
+def test_wavefront_schedule_extended_shade(monkeypatch, mfp, wdist):
+    """The same for the EXT = 1 shade instantiation (mean free path, WDIST)."""
+    monkeypatch.setenv("VR_POOL_SLOTS", "4096")
+    monkeypatch.setenv("VR_TAIL_RAYS", "0")
+    c = common.case("trench")
+    run_pair(c, 100000, mfp=mfp, wdist=wdist)
