@@ -212,6 +212,11 @@ int vr_debug_phase_ms(vr_ctx *ctx, double *ms3, int64_t *launches3);
  * visits, out[1] primitive tests, out[2] neighbour tests, out[3] flux adds,
  * out[4] rays finished by the sky map without a traversal */
 int vr_debug_work_counters(vr_ctx *ctx, uint64_t *out5);
+/* measured read bandwidth of an L2-resident buffer on this device (the
+ * scene of the 1M-disk trench lives in L2, so this, not HBM, is the level its fetches
+ * come from): `bytes` are read `passes` times by a streaming kernel after one warm-up
+ * pass; out2[0] = GB/s, out2[1] = cudaDeviceProp::l2CacheSize in bytes */
+int vr_debug_l2_read_bandwidth(vr_ctx *ctx, uint64_t bytes, int passes, double *out2);
 
 #ifdef __cplusplus
 }

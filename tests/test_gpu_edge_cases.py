@@ -177,3 +177,15 @@ def test_wide_nodes_option(monkeypatch, name, n):
     gg, pg, tg, _, _ = ctx.debug_intersect(probe)
     assert (go == gg).all() and (pr == pg).all() and (to == tg).all()
     ctx.close()
+
+
+def test_l2_read_bandwidth_diagnostic():
+    """vr_debug_l2_read_bandwidth returns a plausible rate (above HBM's, below 100 TB/s) and
+    the device's L2 size; bad arguments are an error, not a crash."""
+    ctx = capi.Context(0)
+    gbps, l2 = ctx.l2_read_bandwidth(32 << 20, 10)
+    assert l2 >= 32 << 20
+    assert 3000.0 < gbps < 100000.0, gbps
+    with pytest.raises(capi.VrError):
+        ctx.l2_read_bandwidth(0, 10)
+    ctx.close()

@@ -24,7 +24,7 @@ EXPORTS = [
     "vr_flux_postprocess",
     "vr_ctx_stream", "vr_ctx_synchronize", "vr_last_kernel_ms", "vr_last_launch_count", "vr_build_neighbors", "vr_free",
     "vr_debug_intersect", "vr_debug_source_rays", "vr_debug_math", "vr_debug_philox",
-    "vr_debug_reflect", "vr_debug_bvh_stats", "vr_debug_work_counters", "vr_debug_phase_timing",
+    "vr_debug_reflect", "vr_debug_bvh_stats", "vr_debug_work_counters", "vr_debug_l2_read_bandwidth", "vr_debug_phase_timing",
     "vr_debug_phase_ms",
 ]
 
@@ -111,6 +111,7 @@ def lib():
                                        C.c_uint64, C.c_uint32, _vp]
         L.vr_debug_bvh_stats.argtypes = [_vp, _vp]
         L.vr_debug_work_counters.argtypes = [_vp, _vp]
+        L.vr_debug_l2_read_bandwidth.argtypes = [_vp, C.c_uint64, C.c_int, _vp]
         L.vr_debug_phase_timing.argtypes = [_vp, C.c_int]
         L.vr_debug_phase_ms.argtypes = [_vp, _vp, _vp]
         _lib = L
@@ -341,6 +342,12 @@ class Context:
         self._ck(self.L.vr_debug_phase_ms(self.h, _p(ms), _p(n)))
         return {"traverse_ms": float(ms[0]), "shade_ms": float(ms[1]), "other_ms": float(ms[2]),
                 "traverse_launches": int(n[0]), "shade_launches": int(n[1])}
+
+    def l2_read_bandwidth(self, nbytes=48 << 20, passes=20):
+        """(GB/s read from an L2-resident buffer, L2 size in bytes) -- vr_debug_l2_read_bandwidth"""
+        out = np.zeros(2, np.float64)
+        self._ck(self.L.vr_debug_l2_read_bandwidth(self.h, int(nbytes), int(passes), _p(out)))
+        return float(out[0]), int(out[1])
 
     def work_counters(self):
         out = np.zeros(5, np.uint64)

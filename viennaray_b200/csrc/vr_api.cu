@@ -1233,4 +1233,17 @@ int vr_debug_work_counters(vr_ctx *ctx, uint64_t *out5) {
   return VR_OK;
 }
 
+int vr_debug_l2_read_bandwidth(vr_ctx *ctx, uint64_t bytes, int passes, double *out2) {
+  if (!ctx || !out2 || bytes < 16 || passes < 1)
+    return VR_ERR_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  double gbps = 0.;
+  CK(vr::l2ReadBandwidth((size_t)bytes, passes, ctx->numSMs, ctx->stream, &gbps));
+  out2[0] = gbps;
+  out2[1] = (double)prop.l2CacheSize;
+  return VR_OK;
+}
+
 }  // extern "C"

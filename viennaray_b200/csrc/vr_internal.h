@@ -113,6 +113,8 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
                      const float sceneHi[3], cudaStream_t stream, Bvh *out);
 void freeBvh(Bvh *b, cudaStream_t stream);
 
+cudaError_t l2ReadBandwidth(size_t bytes, int passes, int numSMs, cudaStream_t s, double *gbps);
+
 // ---- scene preparation (vr_scene.cu) ----------------------------------------
 cudaError_t launchPackDiskNormals(const float *nxyz, uint32_t n, float4 *B, cudaStream_t s);
 cudaError_t launchPackTriangles(const float *verts, const uint32_t *tris, const float *normals,

@@ -507,4 +507,70 @@ cudaError_t remapNeighbors(const uint32_t *s2o, const uint32_t *offO, const uint
   return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------
+// L2 read bandwidth (diagnostic for the roofline: SURVEY 8d).  A persistent grid streams a
+// buffer that fits L2 with 16-byte ld.global.cg loads (cached in L2 only), four
+// independent loads in flight per thread.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2ReadKernel(const uint4 *buf, size_t n, int passes,
+                                                    unsigned int *sink) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+  for (int pass = 0; pass < passes; ++pass) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+      const uint4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride),
+                  c = __ldcg(buf + i + 2 * stride), d = __ldcg(buf + i + 3 * stride);
+      acc.x ^= a.x ^ b.x ^ c.x ^ d.x;
+      acc.y ^= a.y ^ b.y ^ c.y ^ d.y;
+      acc.z ^= a.z ^ b.z ^ c.z ^ d.z;
+      acc.w ^= a.w ^ b.w ^ c.w ^ d.w;
+    }
+    for (; i < n; i += stride) {
+      const uint4 a = __ldcg(buf + i);
+      acc.x ^= a.x;
+      acc.y ^= a.y;
+      acc.z ^= a.z;
+      acc.w ^= a.w;
+    }
+  }
+  if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u)  // keeps the loads alive
+    atomicAdd(sink, 1u);
+}
+
+cudaError_t l2ReadBandwidth(size_t bytes, int passes, int numSMs, cudaStream_t s, double *gbps) {
+  const size_t n = bytes / sizeof(uint4);
+  if (n == 0 || passes < 1)
+    return cudaErrorInvalidValue;
+  uint4 *buf = nullptr;
+  unsigned int *sink = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e;
+  if ((e = cudaMalloc(&buf, n * sizeof(uint4))) != cudaSuccess)
+    return e;
+  if ((e = cudaMalloc(&sink, sizeof(unsigned int))) == cudaSuccess &&
+      (e = cudaMemsetAsync(buf, 0x5a, n * sizeof(uint4), s)) == cudaSuccess &&
+      (e = cudaMemsetAsync(sink, 0, sizeof(unsigned int), s)) == cudaSuccess &&
+      (e = cudaEventCreate(&e0)) == cudaSuccess && (e = cudaEventCreate(&e1)) == cudaSuccess) {
+    const int grid = numSMs * 8;
+    l2ReadKernel<<<grid, 256, 0, s>>>(buf, n, 2, sink);  // warm-up: pulls the buffer into L2
+    cudaEventRecord(e0, s);
+    l2ReadKernel<<<grid, 256, 0, s>>>(buf, n, passes, sink);
+    cudaEventRecord(e1, s);
+    if ((e = cudaEventSynchronize(e1)) == cudaSuccess && (e = cudaGetLastError()) == cudaSuccess) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      *gbps = (double)(n * sizeof(uint4)) * passes / (ms * 1e-3) / 1e9;
+    }
+  }
+  if (e0)
+    cudaEventDestroy(e0);
+  if (e1)
+    cudaEventDestroy(e1);
+  cudaFree(sink);
+  cudaFree(buf);
+  return e;
+}
+
 }  // namespace vr
