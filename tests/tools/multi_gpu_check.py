@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N scripts/multi_gpu_check.py
+"""torchrun --nproc-per-node N tests/tools/multi_gpu_check.py
 Every rank traces its contiguous ray-index shard of ONE job on its own GPU,
 the fixed-point flux words + counters are summed with one NCCL all-reduce, and
 rank 0 checks the result bit-for-bit against the CPU oracle's whole-job flux
@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tests import common  # noqa: E402
 from viennaray_b200 import capi, host  # noqa: E402
 from viennaray_b200 import distributed as vd  # noqa: E402
