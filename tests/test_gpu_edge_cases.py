@@ -21,9 +21,9 @@ def tiny_case(n):
                 bc=[0, 1, 2], source_dir=host.POS_Z, kind=0, sticking=0.4, power=1.0, cone=0.0)
 
 
-@pytest.mark.parametrize("n", [1, 2, 4, 5, 9])
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 8, 9, 17])
 def test_tiny_scenes(n):
-    """n <= 4: the whole BVH is one leaf reference; n = 5: the first inner node."""
+    """n <= 8 (VR_LEAF_MAX): the whole BVH is one leaf reference; n = 9: the first inner node."""
     c = tiny_case(n)
     orc = common.make_oracle(c)
     ctx, src, _ = common.make_gpu(c)
@@ -156,7 +156,7 @@ def test_scene_far_from_the_origin(shift):
 
 
 @pytest.mark.parametrize("name", ["trench", "triangle3D"])
-@pytest.mark.parametrize("n", [0, 3, 5, 9])
+@pytest.mark.parametrize("n", [0, 3, 9, 17, 40])
 def test_wide_nodes_option(monkeypatch, name, n):
     """VR_BVH_WIDE=1 (4-wide nodes, read when the scene is committed) changes the order of the
     traversal only: IDs, t and the whole-walk flux words stay those of the oracle.  n > 0:

@@ -8,7 +8,7 @@
 #define VR_INVALID_ID 0xffffffffu
 #define VR_TNEAR 1e-4f            // fillRayPosition default (rayUtil.hpp:218)
 #ifndef VR_LEAF_MAX
-#define VR_LEAF_MAX 4u  // primitives per BVH leaf (<= 15)
+#define VR_LEAF_MAX 8u  // primitives per BVH leaf (<= 15; 8 measured best once the disk test lost its slow path)
 #endif
 #define VR_DONE 0x7fffffffu  // traversal finished / unused child (not a valid node index)
 #define VR_LEAF_FLAG 0x80000000u  // child reference: leaf(first << 4 | count)
