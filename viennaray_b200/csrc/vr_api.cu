@@ -600,7 +600,8 @@ int vr_scene_commit(vr_ctx *ctx) {
     CKT(launchPackDiskNormals(ctx->dNxyz, n, B, st));
     CKT(launchDiskBounds(A, B, n, lo, hi, st));
   }
-  CKT(buildBvh(lo, hi, n, ctx->geoLo, ctx->geoHi, st, &ctx->bvh));
+  CKT(buildBvh(lo, hi, n, ctx->geoLo, ctx->geoHi, tri ? VR_LEAF_MAX_TRI : VR_LEAF_MAX,
+               st, &ctx->bvh));
   const size_t per = tri ? 4 : 2;  // float4 records per primitive
   CKT(cudaMallocAsync(&ctx->dPrim, sizeof(float4) * per * n, st));
   CKT(launchGatherPrims(ctx->geoType, A, B, C, N, ctx->bvh.sortedToOrig, n, ctx->dPrim, st));

@@ -132,9 +132,10 @@ __global__ void refitKernel(const float4 *lo, const float4 *hi, const uint32_t *
   }
 }
 
-__device__ __forceinline__ uint32_t childRef(int first, int last, int internalIdx) {
+__device__ __forceinline__ uint32_t childRef(int first, int last, int internalIdx,
+                                             uint32_t leafMax) {
   uint32_t cnt = (uint32_t)(last - first + 1);
-  if (cnt <= VR_LEAF_MAX)
+  if (cnt <= leafMax)
     return VR_LEAF_FLAG | ((uint32_t)first << 4) | cnt;
   return (uint32_t)internalIdx;
 }
@@ -162,11 +163,11 @@ __device__ __forceinline__ void emitNode(int i, const float4 *lo, const float4 *
                                          const float4 *nodeHi, Node2 *nodes, float3 qLo,
                                          float3 qInv, double *sah, double &aIn, double &aLeaf,
                                          unsigned &cNodes, unsigned &cLeaves,
-                                         unsigned &cMaxLeaf) {
+                                         unsigned &cMaxLeaf, uint32_t leafMax) {
   if (i >= n - 1)
     return;
   int2 r = range[i];
-  if ((uint32_t)(r.y - r.x + 1) <= VR_LEAF_MAX && i != 0)
+  if ((uint32_t)(r.y - r.x + 1) <= leafMax && i != 0)
     return;  // inside a collapsed leaf (never referenced)
   int g = split[i];
   float4 l0, h0, l1, h1;
@@ -180,7 +181,7 @@ __device__ __forceinline__ void emitNode(int i, const float4 *lo, const float4 *
     l0 = nodeLo[g];
     h0 = nodeHi[g];
     int2 rc = range[g];
-    ref0 = childRef(rc.x, rc.y, g);
+    ref0 = childRef(rc.x, rc.y, g, leafMax);
   }
   if (r.y == g + 1) {
     uint32_t p = sorted[g + 1];
@@ -191,7 +192,7 @@ __device__ __forceinline__ void emitNode(int i, const float4 *lo, const float4 *
     l1 = nodeLo[g + 1];
     h1 = nodeHi[g + 1];
     int2 rc = range[g + 1];
-    ref1 = childRef(rc.x, rc.y, g + 1);
+    ref1 = childRef(rc.x, rc.y, g + 1, leafMax);
   }
   Node2 nd;
   nd.c0 = quantizeChild(l0, h0, qLo, qInv, ref0);
@@ -223,11 +224,11 @@ __device__ __forceinline__ void emitNode(int i, const float4 *lo, const float4 *
 __global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
                            const int2 *range, const int *split, const float4 *nodeLo,
                            const float4 *nodeHi, Node2 *nodes, unsigned int *stats, float3 qLo,
-                           float3 qInv, double *sah) {
+                           float3 qInv, double *sah, uint32_t leafMax) {
   double aIn = 0., aLeaf = 0.;
   unsigned cNodes = 0u, cLeaves = 0u, cMaxLeaf = 0u;
   emitNode(blockIdx.x * blockDim.x + threadIdx.x, lo, hi, sorted, n, range, split, nodeLo, nodeHi,
-           nodes, qLo, qInv, sah, aIn, aLeaf, cNodes, cLeaves, cMaxLeaf);
+           nodes, qLo, qInv, sah, aIn, aLeaf, cNodes, cLeaves, cMaxLeaf, leafMax);
   // statistics and SAH terms summed per warp first: a million atomics on one address
   // serialise
   cNodes = __reduce_add_sync(0xffffffffu, cNodes);
@@ -261,7 +262,7 @@ struct ChildBox {
 __device__ __forceinline__ ChildBox childOf(int i, int side, const float4 *lo, const float4 *hi,
                                             const uint32_t *sorted, const int2 *range,
                                             const int *split, const float4 *nodeLo,
-                                            const float4 *nodeHi) {
+                                            const float4 *nodeHi, uint32_t leafMax) {
   const int2 r = range[i];
   const int c = split[i] + side;
   const bool single = side == 0 ? (r.x == c) : (r.y == c);
@@ -275,30 +276,31 @@ __device__ __forceinline__ ChildBox childOf(int i, int side, const float4 *lo, c
     b.lo = nodeLo[c];
     b.hi = nodeHi[c];
     const int2 rc = range[c];
-    b.ref = childRef(rc.x, rc.y, c);
+    b.ref = childRef(rc.x, rc.y, c, leafMax);
   }
   return b;
 }
 
 __global__ void emit4Kernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
                             const int2 *range, const int *split, const float4 *nodeLo,
-                            const float4 *nodeHi, uint4 *nodes4, float3 qLo, float3 qInv) {
+                            const float4 *nodeHi, uint4 *nodes4, float3 qLo, float3 qInv,
+                            uint32_t leafMax) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1)
     return;
   const int2 r = range[i];
-  if ((uint32_t)(r.y - r.x + 1) <= VR_LEAF_MAX && i != 0)
+  if ((uint32_t)(r.y - r.x + 1) <= leafMax && i != 0)
     return;
   uint4 e[4];
   int k = 0;
   for (int side = 0; side < 2; ++side) {
-    const ChildBox b = childOf(i, side, lo, hi, sorted, range, split, nodeLo, nodeHi);
+    const ChildBox b = childOf(i, side, lo, hi, sorted, range, split, nodeLo, nodeHi, leafMax);
     if (b.ref & VR_LEAF_FLAG) {
       e[k++] = quantizeChild(b.lo, b.hi, qLo, qInv, b.ref);
     } else {
       for (int s2 = 0; s2 < 2; ++s2) {
         const ChildBox g =
-            childOf((int)b.ref, s2, lo, hi, sorted, range, split, nodeLo, nodeHi);
+            childOf((int)b.ref, s2, lo, hi, sorted, range, split, nodeLo, nodeHi, leafMax);
         e[k++] = quantizeChild(g.lo, g.hi, qLo, qInv, g.ref);
       }
     }
@@ -323,7 +325,7 @@ __global__ void emit4Kernel(const float4 *lo, const float4 *hi, const uint32_t *
 // one LBVH over Morton codes computed with the per-axis scales sInv
 static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t n,
                             const float sceneLo[3], const float sceneHi[3], float3 sInv,
-                            cudaStream_t stream, Bvh *out) {
+                            uint32_t leafMax, cudaStream_t stream, Bvh *out) {
   freeBvh(out, stream);
   const bool wide = getenv("VR_BVH_WIDE") && atoi(getenv("VR_BVH_WIDE")) > 0;
   unsigned long long *keys = nullptr, *keysSorted = nullptr;
@@ -391,7 +393,7 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
   VR_CK(cudaMallocAsync(&tmp, tmpBytes ? tmpBytes : 16, stream));
   VR_CK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, out->sortedToOrig,
                                         (int)n, 0, 63, stream));
-  if (n <= VR_LEAF_MAX) {
+  if (n <= leafMax) {
     out->rootRef = VR_LEAF_FLAG | (0u << 4) | n;
     out->numNodes = 0;
     out->numLeaves = 1;
@@ -419,13 +421,13 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
     VR_CK(cudaGetLastError());
     emitKernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(primLo, primHi, out->sortedToOrig, (int)n,
                                                       range, split, nodeLo, nodeHi, out->nodes,
-                                                      stats, qLo, qInv, sah);
+                                                      stats, qLo, qInv, sah, leafMax);
     VR_CK(cudaGetLastError());
     if (wide) {
       VR_CK(cudaMallocAsync(&out->nodes4, sizeof(uint4) * 4 * (size_t)(n - 1), stream));
       emit4Kernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(primLo, primHi, out->sortedToOrig, (int)n,
                                                          range, split, nodeLo, nodeHi,
-                                                         out->nodes4, qLo, qInv);
+                                                         out->nodes4, qLo, qInv, leafMax);
       VR_CK(cudaGetLastError());
     }
     unsigned int hs[4];
@@ -454,7 +456,7 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
 // (cost = sum of inner-node areas + 0.4 x sum of leaf areas x primitives; 0.4 is the
 // measured instruction ratio of a disk test to a node visit).
 cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, const float sceneLo[3],
-                     const float sceneHi[3], cudaStream_t stream, Bvh *out) {
+                     const float sceneHi[3], uint32_t leafMax, cudaStream_t stream, Bvh *out) {
   float ext[3], maxExt = 0.f;
   for (int a = 0; a < 3; ++a) {
     ext[a] = sceneHi[a] - sceneLo[a];
@@ -479,7 +481,7 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
       inv[a] = ext[a] > 0.f ? 1.f / (powf(ext[a], alphas[k]) * powf(maxExt, 1.f - alphas[k])) : 0.f;
     Bvh cand;
     err = buildOne(primLo, primHi, n, sceneLo, sceneHi, make_float3(inv[0], inv[1], inv[2]),
-                   stream, &cand);
+                   leafMax, stream, &cand);
     if (err != cudaSuccess) {
       freeBvh(&cand, stream);
       break;
@@ -495,7 +497,7 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
     } else {
       freeBvh(&cand, stream);
     }
-    if (n <= VR_LEAF_MAX)
+    if (n <= leafMax)
       break;  // a single leaf: nothing to choose
   }
   cudaEventRecord(e1, stream);

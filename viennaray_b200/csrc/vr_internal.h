@@ -7,8 +7,13 @@
 
 #define VR_INVALID_ID 0xffffffffu
 #define VR_TNEAR 1e-4f            // fillRayPosition default (rayUtil.hpp:218)
+// primitives per BVH leaf (<= 15): 8 disks measured best once the disk test lost its
+// division slow path; a triangle test costs twice a disk test and 4 stay best there
 #ifndef VR_LEAF_MAX
-#define VR_LEAF_MAX 8u  // primitives per BVH leaf (<= 15; 8 measured best once the disk test lost its slow path)
+#define VR_LEAF_MAX 8u
+#endif
+#ifndef VR_LEAF_MAX_TRI
+#define VR_LEAF_MAX_TRI 4u
 #endif
 #define VR_DONE 0x7fffffffu  // traversal finished / unused child (not a valid node index)
 #define VR_LEAF_FLAG 0x80000000u  // child reference: leaf(first << 4 | count)
@@ -110,7 +115,7 @@ struct Bvh {
                                         // primitive counts, both over the root area
 };
 cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, const float sceneLo[3],
-                     const float sceneHi[3], cudaStream_t stream, Bvh *out);
+                     const float sceneHi[3], uint32_t leafMax, cudaStream_t stream, Bvh *out);
 void freeBvh(Bvh *b, cudaStream_t stream);
 
 cudaError_t l2ReadBandwidth(size_t bytes, int passes, int numSMs, cudaStream_t s, double *gbps);
