@@ -22,6 +22,11 @@
 
 namespace vr {
 
+// Traversal stack: the radix tree over 63-bit Morton keys, ties broken by the 32-bit index,
+// is at most 63 + 32 levels deep and a binary descent pushes at most one entry per level,
+// so 96 entries cannot overflow (the bounds checks at the pushes are belt and braces; the
+// optional 4-wide variant pushes up to three per level and relies on real trees being far
+// shallower than that bound).
 #define VR_STACK 96
 #ifndef VR_NODE_MIN
 #define VR_NODE_MIN 1  // lanes at inner nodes needed to keep the warp in the node loop
