@@ -170,3 +170,16 @@ def test_wavefront_schedule_extended_shade(monkeypatch, mfp, wdist):
     monkeypatch.setenv("VR_TAIL_RAYS", "0")
     c = common.case("trench")
     run_pair(c, 100000, mfp=mfp, wdist=wdist)
+
+
+@pytest.mark.parametrize("name", ["trench", "trench_ion", "holes", "disk3D"])
+@pytest.mark.parametrize("tail", [0, 262144])
+def test_spread_kernel_option(monkeypatch, name, tail):
+    """VR_SPREAD_SPLIT=1: the shade kernel queues every geometry hit and spreadKernel does the
+    neighbour tests and the flux adds afterwards (the default for scenes that do not fit L2).
+    Integer sums: flux words and counters must not change."""
+    monkeypatch.setenv("VR_SPREAD_SPLIT", "1")
+    monkeypatch.setenv("VR_TAIL_RAYS", str(tail))
+    monkeypatch.setenv("VR_POOL_SLOTS", "16384")
+    c = common.case(name)
+    run_pair(c, 150000)

@@ -98,6 +98,11 @@ struct TraceParams {
   unsigned int *slotCursor;      // traverse kernel: next slot
   unsigned int *liveCount;       // shade kernel: slots still alive afterwards
   unsigned long long *work;      // optional work counters (4) or null
+  // optional neighbour-spread queue (disks, default shade instantiation): the shade kernel
+  // appends {org, weight}, {dir, hit disk} per geometry hit and spreadKernel distributes the
+  // flux afterwards; null: the spread runs inside the shade kernel
+  float4 *spreadQ;
+  unsigned int *spreadCount;
 };
 
 // ---- acceleration structure (vr_bvh.cu) ----------------------------------
@@ -158,6 +163,7 @@ cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s);
 cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s);
 cudaError_t launchShade(const TraceParams &p, cudaStream_t s);
 // the last rays of a trace, each run to its end by one thread (compacted pool in p.pool)
+cudaError_t launchSpread(const TraceParams &p, int numSMs, cudaStream_t s);
 cudaError_t launchTail(const TraceParams &p, cudaStream_t s);
 // between iterations: resets the cursors; compact mode: slotCount = liveCount
 cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int compact,

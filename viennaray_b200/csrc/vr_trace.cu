@@ -41,6 +41,9 @@ namespace vr {
 #define VR_TRAV_BLOCKS_WIDE 10  // the same for the 4-wide node variant
 #endif
 #define VR_WDIST_CAP 64  // disks one ray can hit at once (hit disk + its neighbour list)
+#ifndef VR_SHADE_BLOCKS_Q
+#define VR_SHADE_BLOCKS_Q 4
+#endif
 #ifndef VR_SHADE_BLOCKS
 #define VR_SHADE_BLOCKS 4
 #endif
@@ -657,7 +660,7 @@ struct Tally {
 // EXT == 1 adds the two optional features that are off in the default
 // instantiation: mean-free-path scattering (rayTraceKernel.hpp:179-203) and the
 // distance-weighted neighbour spread of VIENNARAY_USE_WDIST (:258-296).
-template <int D, int GEO, int EXT>
+template <int D, int GEO, int EXT, int Q>
 __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, const float ht,
                                          const uint32_t hprim, const uint32_t hgeom, Tally &c) {
   const DeviceScene &sc = p.scene;
@@ -757,6 +760,11 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, cons
           atomicAdd(&p.flux[ids[k]], toFixed(((w / dist[k]) / invSum) * (float)nh));
           ++wFlux;
         }
+      } else if (Q) {
+        // :271-306 handed to spreadKernel: {org, weight}, {dir, hit disk}
+        const unsigned q = atomicAdd(p.spreadCount, 1u);
+        p.spreadQ[2 * (size_t)q] = make_float4(org.x, org.y, org.z, w);
+        p.spreadQ[2 * (size_t)q + 1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(hprim));
       } else {
         const unsigned long long wf = toFixed(w);
         atomicAdd(&p.flux[hprim], wf);  // :297-306 surfaceCollision
@@ -851,8 +859,8 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, cons
   return finish;
 }
 
-template <int D, int GEO, int EXT>
-__global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid_constant__ TraceParams p) {
+template <int D, int GEO, int EXT, int Q>
+__global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) shadeKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t numSlots = *p.slotCount;
@@ -902,7 +910,7 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
     hitFromBack = (meta.w >> 31) != 0u;
     w = __ldcs(&p.pool.weight[s]);
     rs = __ldcs(&p.pool.rng[s]);  // issued with the other pool loads, not after the neighbour gathers
-    finish = shadeHit<D, GEO, EXT>(p, r, hv.x, __float_as_uint(hv.y), __float_as_uint(hv.z), c);
+    finish = shadeHit<D, GEO, EXT, Q>(p, r, hv.x, __float_as_uint(hv.y), __float_as_uint(hv.z), c);
   }
 
   // ---- regenerate finished slots; write survivors back (in place, or appended to
@@ -992,6 +1000,64 @@ __global__ void __launch_bounds__(256, VR_SHADE_BLOCKS) shadeKernel(const __grid
   }
 }
 
+// Neighbour spread as its own pass (rayTraceKernel.hpp:255-306): one thread per queued
+// geometry hit, all lanes busy, the same tests and the same fixed-point adds as the inline
+// version (integer sums: the order of the adds does not matter).
+__global__ void __launch_bounds__(256) spreadKernel(const __grid_constant__ TraceParams p) {
+  const DeviceScene &sc = p.scene;
+  const unsigned n = *p.spreadCount;
+  unsigned wNb = 0, wFlux = 0;
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    float4 a, b;
+    ldg256(p.spreadQ + 2 * (size_t)q, a, b);
+    const V3 org = {a.x, a.y, a.z}, dir = {b.x, b.y, b.z};
+    const uint32_t hprim = __float_as_uint(b.w);
+    const unsigned long long wf = toFixed(a.w);
+    atomicAdd(&p.flux[hprim], wf);
+    ++wFlux;
+    const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
+    for (uint32_t k = k0; k < k1; k += 4) {
+      uint32_t id[4];
+      float4 P[4], Nn[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (id[j] != VR_INVALID_ID)
+          ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (id[j] != VR_INVALID_ID) {
+          ++wNb;
+          if (checkLocal(P[j], Nn[j], org, dir)) {
+            atomicAdd(&p.flux[id[j]], wf);
+            ++wFlux;
+          }
+        }
+    }
+  }
+  if (p.work) {
+    const unsigned a = __reduce_add_sync(0xffffffffu, wNb), b = __reduce_add_sync(0xffffffffu, wFlux);
+    if ((threadIdx.x & 31u) == 0) {
+      atomicAdd(&p.work[2], (unsigned long long)a);
+      atomicAdd(&p.work[3], (unsigned long long)b);
+    }
+  }
+}
+
+cudaError_t launchSpread(const TraceParams &p, int numSMs, cudaStream_t s) {
+  if (!p.spreadQ || p.numSlots == 0 || p.scene.geoType != 0 || p.scene.D != 3 ||
+      p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST))
+    return cudaSuccess;
+  unsigned grid = (p.numSlots + 255u) / 256u;
+  const unsigned cap = (unsigned)numSMs * 8u;
+  if (grid > cap)
+    grid = cap;
+  spreadKernel<<<grid, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
 // The thin tail of a trace: once the source is exhausted and only a few
 // thousand rays are left, every remaining ray is run to its end by one thread
 // of ONE launch -- traverse and shade in a loop -- instead of ~1000 iterations
@@ -1036,7 +1102,7 @@ __global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ TraceP
         r.bh = boundaryTest(sc, r.org, r.dir);
       Hit best = r.bh;
       traverseOne<GEO>(sc, r.org, r.dir, best, wNodes, wPrims);
-      if (shadeHit<D, GEO, EXT>(p, r, best.t, best.prim, best.geom, c))
+      if (shadeHit<D, GEO, EXT, 0>(p, r, best.t, best.prim, best.geom, c))
         break;
     }
   }
@@ -1102,6 +1168,7 @@ __global__ void flipKernel(unsigned int *ctrl, unsigned long long *counters, int
   if (threadIdx.x == 0) {
     const unsigned int live = compact ? ctrl[1] : (unsigned int)v;
     ctrl[3] = live;
+    ctrl[4] = 0u;  // neighbour-spread queue
     ctrl[0] = 0u;
     if (compact)
       ctrl[2] = live;
@@ -1117,14 +1184,16 @@ cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int com
 template <int EXT> static void launchShadeExt(const TraceParams &p, unsigned grid, cudaStream_t s) {
   if (p.scene.geoType == 0) {
     if (p.scene.D == 2)
-      shadeKernel<2, 0, EXT><<<grid, 256, 0, s>>>(p);
+      shadeKernel<2, 0, EXT, 0><<<grid, 256, 0, s>>>(p);
+    else if (!EXT && p.spreadQ)  // neighbour spread queued for spreadKernel
+      shadeKernel<3, 0, 0, 1><<<grid, 256, 0, s>>>(p);
     else
-      shadeKernel<3, 0, EXT><<<grid, 256, 0, s>>>(p);
+      shadeKernel<3, 0, EXT, 0><<<grid, 256, 0, s>>>(p);
   } else {
     if (p.scene.D == 2)
-      shadeKernel<2, 1, EXT><<<grid, 256, 0, s>>>(p);
+      shadeKernel<2, 1, EXT, 0><<<grid, 256, 0, s>>>(p);
     else
-      shadeKernel<3, 1, EXT><<<grid, 256, 0, s>>>(p);
+      shadeKernel<3, 1, EXT, 0><<<grid, 256, 0, s>>>(p);
   }
 }
 
