@@ -11,6 +11,9 @@
 //                   regeneration of finished rays from the source
 //                   (rayTraceKernel.hpp:120-143).
 //
+//   spreadKernel    optional (scenes larger than L2): the neighbour spread of the queued
+//                   geometry hits as its own pass with every lane busy.
+//
 //   tailKernel      once the source is dry and few rays survive: one thread per
 //                   ray runs traverse + shade in a loop to the ray's end, in one
 //                   launch (replaces ~1000 iterations of tiny launches).
