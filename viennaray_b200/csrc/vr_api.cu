@@ -80,6 +80,9 @@ struct vr_ctx {
   uint32_t spreadCap = 0;
   int spreadMode = -1;
   size_t l2Bytes = 0;
+  float alphaLast = 1.f;  // Morton cell shape of the last full search (vr_scene_commit)
+  uint32_t alphaN = 0;
+  int alphaGeo = -1, alphaAge = 0;
 };
 
 static std::string g_createError;
@@ -614,8 +617,23 @@ int vr_scene_commit(vr_ctx *ctx) {
     CKT(launchPackDiskNormals(ctx->dNxyz, n, B, st));
     CKT(launchDiskBounds(A, B, n, lo, hi, st));
   }
-  CKT(buildBvh(lo, hi, n, ctx->geoLo, ctx->geoHi, tri ? VR_LEAF_MAX_TRI : VR_LEAF_MAX,
+  // A time-stepping caller commits a slowly changing scene over and over: the Morton cell
+  // shape the full three-way search picked is reused while the primitive count stays within
+  // 1/8 of that scene's, and searched again every 16th commit
+  float alphaHint = -1.f;
+  if (ctx->alphaN && ctx->alphaGeo == ctx->geoType && ctx->alphaAge < 16 &&
+      (n > ctx->alphaN ? n - ctx->alphaN : ctx->alphaN - n) <= ctx->alphaN / 8)
+    alphaHint = ctx->alphaLast;
+  CKT(buildBvh(lo, hi, n, ctx->geoLo, ctx->geoHi, tri ? VR_LEAF_MAX_TRI : VR_LEAF_MAX, alphaHint,
                st, &ctx->bvh));
+  if (alphaHint < 0.f) {
+    ctx->alphaLast = ctx->bvh.mortonAlpha;
+    ctx->alphaN = n;
+    ctx->alphaGeo = ctx->geoType;
+    ctx->alphaAge = 0;
+  } else {
+    ++ctx->alphaAge;
+  }
   const size_t per = tri ? 4 : 2;  // float4 records per primitive
   CKT(cudaMallocAsync(&ctx->dPrim, sizeof(float4) * per * n, st));
   CKT(launchGatherPrims(ctx->geoType, A, B, C, N, ctx->bvh.sortedToOrig, n, ctx->dPrim, st));

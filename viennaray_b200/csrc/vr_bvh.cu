@@ -456,7 +456,8 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
 // (cost = sum of inner-node areas + 0.4 x sum of leaf areas x primitives; 0.4 is the
 // measured instruction ratio of a disk test to a node visit).
 cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, const float sceneLo[3],
-                     const float sceneHi[3], uint32_t leafMax, cudaStream_t stream, Bvh *out) {
+                     const float sceneHi[3], uint32_t leafMax, float alphaHint, cudaStream_t stream,
+                     Bvh *out) {
   float ext[3], maxExt = 0.f;
   for (int a = 0; a < 3; ++a) {
     ext[a] = sceneHi[a] - sceneLo[a];
@@ -466,6 +467,9 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
   int numAlpha = 3;
   if (const char *fa = getenv("VR_MORTON_ALPHA")) {
     alphas[0] = (float)atof(fa);
+    numAlpha = 1;
+  } else if (alphaHint >= 0.f) {  // the shape the caller's previous, similar scene settled on
+    alphas[0] = alphaHint;
     numAlpha = 1;
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;

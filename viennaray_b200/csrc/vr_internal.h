@@ -120,7 +120,8 @@ struct Bvh {
                                         // primitive counts, both over the root area
 };
 cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, const float sceneLo[3],
-                     const float sceneHi[3], uint32_t leafMax, cudaStream_t stream, Bvh *out);
+                     const float sceneHi[3], uint32_t leafMax, float alphaHint, cudaStream_t stream,
+                     Bvh *out);
 void freeBvh(Bvh *b, cudaStream_t stream);
 
 cudaError_t l2ReadBandwidth(size_t bytes, int passes, int numSMs, cudaStream_t s, double *gbps);
