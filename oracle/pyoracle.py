@@ -36,7 +36,19 @@ def build(reference_root="/root/reference"):
 
 class Particle(C.Structure):
     _fields_ = [("kind", C.c_int), ("sticking", C.c_float), ("sourcePower", C.c_float),
-                ("coneMinAngle", C.c_float), ("meanFreePath", C.c_float)]
+                ("coneMinAngle", C.c_float), ("meanFreePath", C.c_float),
+                ("stickingByMaterial", _vp), ("numMaterials", C.c_int)]
+
+    def set_sticking_by_material(self, table):
+        """sticking[materialId] of the hit primitive; None returns to the constant."""
+        if table is None:
+            self._table = None
+            self.stickingByMaterial, self.numMaterials = None, 0
+            return self
+        self._table = np.ascontiguousarray(table, np.float32)  # kept alive with the struct
+        self.stickingByMaterial = self._table.ctypes.data
+        self.numMaterials = len(self._table)
+        return self
 
 
 class Config(C.Structure):
@@ -60,7 +72,7 @@ REFLECTIVE, PERIODIC, IGNORE = 0, 1, 2
 POS_X, NEG_X, POS_Y, NEG_Y, POS_Z, NEG_Z = range(6)
 
 _oracle = None
-_ref = None
+_ref = {}
 
 
 def oracle_lib():
@@ -76,6 +88,7 @@ def oracle_lib():
         L.vro_scene_set_disks.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_float]
         L.vro_scene_set_triangles.argtypes = [_vp, _vp, C.c_uint32, _vp, C.c_uint32]
         L.vro_scene_setup.argtypes = [_vp, C.c_int, _vp, C.c_float]
+        L.vro_scene_set_material_ids.argtypes = [_vp, _vp]
         L.vro_scene_set_source_grid.argtypes = [_vp, _vp, C.c_uint32]
         L.vro_scene_bbox.argtypes = [_vp, _vp]
         L.vro_scene_num_prims.restype = C.c_uint32
@@ -104,10 +117,14 @@ def have_ref():
     return os.path.exists(os.path.join(_REF, "libvr_ref.so"))
 
 
-def ref_lib():
-    global _ref
-    if _ref is None:
-        L = C.CDLL(os.path.join(_REF, "libvr_ref.so"))
+def have_ref_wdist():
+    return os.path.exists(os.path.join(_REF, "libvr_ref_wdist.so"))
+
+
+def ref_lib(wdist=False):
+    """The reference's unmodified kernel; wdist=True: the build with -DVIENNARAY_USE_WDIST."""
+    if wdist not in _ref:
+        L = C.CDLL(os.path.join(_REF, "libvr_ref_wdist.so" if wdist else "libvr_ref.so"))
         L.ref_trace_disk.argtypes = [C.c_int, _vp, _vp, C.c_uint32, C.c_float, _vp, C.c_int,
                                      C.c_int, C.c_float, C.c_float, C.c_float, C.c_uint64,
                                      C.c_uint64, C.c_uint, C.c_uint, _vp, C.c_int, C.c_int, _vp,
@@ -124,8 +141,30 @@ def ref_lib():
         L.ref_boundary_process_hit.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp,
                                                C.c_uint32, C.c_float]
         L.ref_set_threads.argtypes = [C.c_int]
-        _ref = L
-    return _ref
+        L.ref_set_options.restype = None
+        L.ref_set_options.argtypes = [C.c_float, _vp, C.c_int, _vp, C.c_uint32]
+        assert L.ref_uses_wdist() == (1 if wdist else 0)
+        _ref[wdist] = L
+    return _ref[wdist]
+
+
+class _RefOptions:
+    """Mean free path / sticking table / material IDs for the reference calls inside a
+    ``with`` block (ref_driver.cpp: ref_set_options)."""
+
+    def __init__(self, L, mean_free_path, sticking_by_material, material_ids):
+        self.L = L
+        self.mfp = float(mean_free_path or 0.0)
+        self.tab = None if sticking_by_material is None else \
+            np.ascontiguousarray(sticking_by_material, np.float32)
+        self.ids = None if material_ids is None else np.ascontiguousarray(material_ids, np.int32)
+
+    def __enter__(self):
+        self.L.ref_set_options(self.mfp, _p(self.tab), 0 if self.tab is None else len(self.tab),
+                               _p(self.ids), 0 if self.ids is None else len(self.ids))
+
+    def __exit__(self, *a):
+        self.L.ref_set_options(0.0, None, 0, None, 0)
 
 
 def disk_factor(D):
@@ -160,6 +199,14 @@ class OracleScene:
         self.n = len(tris)
         self.geo = "triangle"
         self.L.vro_scene_set_triangles(self.h, _p(verts), len(verts), _p(tris), self.n)
+
+    def set_material_ids(self, ids):
+        if ids is None:
+            self.L.vro_scene_set_material_ids(self.h, None)
+            return
+        ids = np.ascontiguousarray(ids, np.int32)
+        assert len(ids) == self.n
+        self.L.vro_scene_set_material_ids(self.h, _p(ids))
 
     def setup(self, source_dir, bc, source_offset):
         bc = (C.c_int * 3)(*(list(bc) + [IGNORE] * 3)[:3])
@@ -260,8 +307,9 @@ class OracleScene:
 
 def ref_trace_disk(D, points, normals, grid_delta, bc, source_dir, kind, sticking, source_power=1.0,
                    cone_min_angle=0.0, rays_per_point=0, rays_fixed=0, seed=12345, runs=1,
-                   primary_dir=None, normalize=False, smooth=0, threads=None):
-    L = ref_lib()
+                   primary_dir=None, normalize=False, smooth=0, threads=None, wdist=False,
+                   mean_free_path=0.0, sticking_by_material=None, material_ids=None):
+    L = ref_lib(wdist)
     if threads:
         L.ref_set_threads(threads)
     points = np.ascontiguousarray(points, np.float32)
@@ -272,16 +320,19 @@ def ref_trace_disk(D, points, normals, grid_delta, bc, source_dir, kind, stickin
     sec = C.c_double()
     bc = (C.c_int * 3)(*(list(bc) + [IGNORE] * 3)[:3])
     pd = None if primary_dir is None else np.array(primary_dir, np.float32)
-    rc = L.ref_trace_disk(D, _p(points), _p(normals), n, grid_delta, bc, source_dir, kind, sticking,
-                          source_power, cone_min_angle, rays_per_point, rays_fixed, seed, runs,
-                          _p(pd), int(normalize), smooth, _p(flux), _p(info), C.byref(sec))
+    with _RefOptions(L, mean_free_path, sticking_by_material, material_ids):
+        rc = L.ref_trace_disk(D, _p(points), _p(normals), n, grid_delta, bc, source_dir, kind,
+                              sticking, source_power, cone_min_angle, rays_per_point, rays_fixed,
+                              seed, runs, _p(pd), int(normalize), smooth, _p(flux), _p(info),
+                              C.byref(sec))
     assert rc == 0
     return flux, info, sec.value
 
 
 def ref_trace_triangle(verts, tris, grid_delta, bc, source_dir, kind, sticking, source_power=1.0,
                        cone_min_angle=0.0, rays_per_point=0, rays_fixed=0, seed=12345, runs=1,
-                       normalize=False, threads=None):
+                       normalize=False, threads=None, mean_free_path=0.0,
+                       sticking_by_material=None, material_ids=None):
     L = ref_lib()
     if threads:
         L.ref_set_threads(threads)
@@ -292,9 +343,11 @@ def ref_trace_triangle(verts, tris, grid_delta, bc, source_dir, kind, sticking, 
     info = np.zeros(8, np.uint64)
     sec = C.c_double()
     bc = (C.c_int * 3)(*(list(bc) + [IGNORE] * 3)[:3])
-    rc = L.ref_trace_triangle(_p(verts), len(verts), _p(tris), n, grid_delta, bc, source_dir, kind,
-                              sticking, source_power, cone_min_angle, rays_per_point, rays_fixed,
-                              seed, runs, int(normalize), _p(flux), _p(info), C.byref(sec))
+    with _RefOptions(L, mean_free_path, sticking_by_material, material_ids):
+        rc = L.ref_trace_triangle(_p(verts), len(verts), _p(tris), n, grid_delta, bc, source_dir,
+                                  kind, sticking, source_power, cone_min_angle, rays_per_point,
+                                  rays_fixed, seed, runs, int(normalize), _p(flux), _p(info),
+                                  C.byref(sec))
     assert rc == 0
     return flux, info, sec.value
 

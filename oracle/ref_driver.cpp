@@ -58,7 +58,65 @@ struct ParticleDesc {
   float sticking, sourcePower, coneMinAngle;
 };
 
+// Options of the next ref_trace_* calls (ref_set_options): a mean free path > 0 and / or a
+// sticking table indexed by the materialId the kernel hands to surfaceReflection
+// (rayTraceKernel.hpp:310-313), and the material IDs given to the geometry
+// (rayTraceDisk.hpp:96-98).  They select TestParticle below instead of a built-in particle.
+struct Options {
+  float meanFreePath = -1.f;
+  std::vector<float> stickingByMaterial;
+  std::vector<int> materialIds;
+} g_opt;
+
+// A user-side particle, as ViennaPS writes them: the reference's own reflection functions
+// (rayReflection.hpp), a sticking probability looked up by materialId, and a mean free path
+// (rayParticle.hpp:72-74).  No reference logic is restated here.
+template <typename T, int D> class TestParticle : public Particle<TestParticle<T, D>, T> {
+  const int kind_;
+  const T sticking_, power_, minAngle_, meanFreePath_;
+  const std::vector<float> table_;
+
+public:
+  TestParticle(const ParticleDesc &p, const Options &o)
+      : kind_(p.kind), sticking_(p.sticking), power_(p.sourcePower), minAngle_(p.coneMinAngle),
+        meanFreePath_(o.meanFreePath), table_(o.stickingByMaterial) {}
+
+  std::pair<T, Vec3D<T>> surfaceReflection(T, const Vec3D<T> &rayDir, const Vec3D<T> &geomNormal,
+                                           const unsigned int, const int materialId,
+                                           const TracingData<T> *, RNG &rng) final {
+    Vec3D<T> dir;
+    if (kind_ == 0) {
+      dir = ReflectionDiffuse<T, D>(geomNormal, rng);
+    } else if (kind_ == 1) {
+      dir = ReflectionSpecular<T, D>(rayDir, geomNormal);
+    } else {
+      T cosTheta = -DotProduct(rayDir, geomNormal);
+      cosTheta = std::min(std::max(cosTheta, T(0)), T(1));
+      const T cone = T(M_PI_2) - std::min(T(std::acos(cosTheta)), minAngle_);
+      dir = ReflectionConedCosine<T, D>(rayDir, geomNormal, rng, cone);
+    }
+    T st = sticking_;
+    if (materialId >= 0 && materialId < (int)table_.size())
+      st = table_[materialId];
+    return {st, dir};
+  }
+  void surfaceCollision(T rayWeight, const Vec3D<T> &, const Vec3D<T> &, const unsigned int primID,
+                        const int, TracingData<T> &localData, const TracingData<T> *,
+                        RNG &) final {
+    localData.getVectorData(0)[primID] += rayWeight;
+  }
+  T getSourceDistributionPower() const final { return power_; }
+  T getMeanFreePath() const final { return meanFreePath_; }
+  std::vector<std::string> getLocalDataLabels() const final { return {"flux"}; }
+};
+
 template <int D> std::unique_ptr<AbstractParticle<float>> makeParticle(const ParticleDesc &p) {
+  // the reference's DiffuseParticle has a fixed cosine source (rayParticle.hpp:158): a
+  // diffuse particle with another source power (config C5) is a user-side particle too
+  if (p.kind >= 0 && p.kind <= 2 &&
+      (g_opt.meanFreePath > 0.f || !g_opt.stickingByMaterial.empty() ||
+       (p.kind == 0 && p.sourcePower != 1.f)))
+    return std::make_unique<TestParticle<float, D>>(p, g_opt);
   switch (p.kind) {
   case 0:
     return std::make_unique<DiffuseParticle<float, D>>(p.sticking, "flux");
@@ -104,6 +162,8 @@ int traceDisk(const float *points, const float *normals, uint32_t n, float gridD
     return 2;
   TraceDisk<float, D> tracer;
   tracer.setGeometry(pts, nrm, gridDelta);
+  if (g_opt.materialIds.size() == n)
+    tracer.setMaterialIds(g_opt.materialIds);
   tracer.setBoundaryConditions(conds);
   tracer.setSourceDirection(static_cast<TraceDirection>(sourceDir));
   tracer.setParticleType(particle);
@@ -141,6 +201,25 @@ extern "C" {
 
 int ref_max_threads() { return omp_get_max_threads(); }
 void ref_set_threads(int n) { omp_set_num_threads(n); }
+// 1 when this library was compiled with -DVIENNARAY_USE_WDIST (oracle/Makefile, ref_wdist)
+int ref_uses_wdist() {
+#ifdef VIENNARAY_USE_WDIST
+  return 1;
+#else
+  return 0;
+#endif
+}
+// Options of the following ref_trace_* calls; all-default arguments switch them off again.
+// meanFreePath <= 0: none.  stickingByMaterial: numMaterials floats or NULL.  materialIds:
+// numIds ints (must equal the primitive count of the traced geometry) or NULL.
+void ref_set_options(float meanFreePath, const float *stickingByMaterial, int numMaterials,
+                     const int *materialIds, uint32_t numIds) {
+  g_opt.meanFreePath = meanFreePath > 0.f ? meanFreePath : -1.f;
+  g_opt.stickingByMaterial.assign(stickingByMaterial ? stickingByMaterial : nullptr,
+                                  stickingByMaterial ? stickingByMaterial + numMaterials : nullptr);
+  g_opt.materialIds.assign(materialIds ? materialIds : nullptr,
+                           materialIds ? materialIds + numIds : nullptr);
+}
 
 // kind: see ParticleDesc.  bc: BoundaryCondition per axis (rayBoundary.hpp:10-14).
 // sourceDir: TraceDirection (rayUtil.hpp:38-45).  fluxOut: runs x n floats.
@@ -183,6 +262,8 @@ int ref_trace_triangle(const float *verts, uint32_t nVerts, const uint32_t *tris
     return 2;
   TraceTriangle<float, D> tracer;
   tracer.setGeometry(mesh);
+  if (g_opt.materialIds.size() == n)
+    tracer.setMaterialIds(g_opt.materialIds);
   tracer.setBoundaryConditions(conds);
   tracer.setSourceDirection(static_cast<TraceDirection>(sourceDir));
   tracer.setParticleType(particle);

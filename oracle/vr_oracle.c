@@ -230,11 +230,24 @@ struct vro_scene {
   /* optional grid source (raySourceGrid.hpp): origins, n x 3 */
   float *grid;
   uint32_t gridN;
+  /* material IDs, n (rayGeometry.hpp:19-26,54-57); NULL: all 0 */
+  int *matId;
   /* BVH over geometry primitives */
   node_t *nodes;
   uint32_t nNodes;
   uint32_t *primOrder;
 };
+
+/* Geometry::setMaterialIds, rayGeometry.hpp:19-26 (call after the primitives are set) */
+int vro_scene_set_material_ids(vro_scene *s, const int *ids) {
+  free(s->matId);
+  s->matId = NULL;
+  if (ids && s->n) {
+    s->matId = (int *)malloc(sizeof(int) * s->n);
+    memcpy(s->matId, ids, sizeof(int) * s->n);
+  }
+  return 0;
+}
 
 vro_scene *vro_scene_create(int D) {
   vro_scene *s = (vro_scene *)calloc(1, sizeof(vro_scene));
@@ -252,6 +265,7 @@ void vro_scene_destroy(vro_scene *s) {
   free(s->nbIdx);
   free(s->nodes);
   free(s->primOrder);
+  free(s->matId);
   free(s->grid);
   free(s);
 }
@@ -515,6 +529,8 @@ int vro_scene_set_disks(vro_scene *s, const float *points, const float *normals,
   s->geoType = 0;
   s->n = n;
   s->radius = radius;
+  free(s->matId); /* material IDs belong to the primitives just replaced */
+  s->matId = NULL;
   free(s->disk);
   free(s->normal);
   s->disk = (float *)malloc(sizeof(float) * 4 * (n + 1));
@@ -553,6 +569,8 @@ int vro_scene_set_triangles(vro_scene *s, const float *verts, uint32_t nVerts,
   s->geoType = 1;
   s->n = n;
   s->nVerts = nVerts;
+  free(s->matId);
+  s->matId = NULL;
   free(s->verts);
   free(s->tris);
   free(s->normal);
@@ -1153,6 +1171,14 @@ static void trace_one(const vro_scene *s, const vro_particle *p, const vro_confi
     }
     float newDir[3];
     float sticking = surface_reflection(s, p, rayDirection, gn, &rng, newDir); /* :310 */
+    if (p->stickingByMaterial) {
+      /* a particle whose sticking depends on the materialId it is handed
+       * (rayTraceKernel.hpp:310-313, rayParticle.hpp:44-48); IDs outside the table keep
+       * the constant */
+      const int m = s->matId ? s->matId[h.prim] : 0;
+      if (m >= 0 && m < p->numMaterials)
+        sticking = p->stickingByMaterial[m];
+    }
     w -= w * sticking;                                                        /* :316 */
     if (w <= 0.f)
       break;

@@ -42,6 +42,10 @@ typedef struct {
   float sourcePower;  /* cosine exponent of the source (1 = cosine) */
   float coneMinAngle; /* coned cosine: cone = pi/2 - min(incAngle, this) */
   float meanFreePath; /* getMeanFreePath(); <= 0: no scattering (rayTraceKernel.hpp:179) */
+  /* optional sticking per materialId of the hit primitive (the materialId argument of
+   * surfaceReflection, rayParticle.hpp:44-48); NULL: constant sticking */
+  const float *stickingByMaterial;
+  int numMaterials;
 } vro_particle;
 
 typedef struct {
@@ -68,6 +72,7 @@ int vro_scene_set_triangles(vro_scene *s, const float *verts, uint32_t nVerts,
                             const uint32_t *tris, uint32_t n);
 /* sourceOffset: disk radius (rayTraceDisk.hpp:21-23) or gridDelta
  * (rayTraceTriangle.hpp:21-23) */
+int vro_scene_set_material_ids(vro_scene *s, const int *ids /* n, or NULL */);
 int vro_scene_setup(vro_scene *s, int sourceDir, const int *bc, float sourceOffset);
 /* SourceGrid (raySourceGrid.hpp:9-74): origins points[idx % n]; n == 0: random source */
 int vro_scene_set_source_grid(vro_scene *s, const float *points, uint32_t n);

@@ -268,29 +268,47 @@ def _repeat_oracle(s, part, num, seeds):
     return np.asarray(out), info
 
 
-STAT_CASES = [("disk3D", 100), ("triangle3D", 100), ("disk2D", 2000), ("trench_ion", 60)]
+def _first_bounce(orc, rays, prim, t, D, seed=5):
+    """Secondary rays leaving the first hit points in random upward directions."""
+    rng = np.random.default_rng(seed)
+    hitp = rays[:, :3] + rays[:, 3:] * t[:, None]
+    nrm = orc.normals()[prim]
+    d = rng.normal(size=(len(rays), 3)).astype(F)
+    if D == 2:
+        d[:, 2] = 0
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[(d * nrm).sum(1) < 0] *= -1
+    return np.ascontiguousarray(np.concatenate([hitp, d], 1), F)
 
 
-@pytest.mark.parametrize("name,rays_per_prim", STAT_CASES)
-def test_flux_statistical_parity_with_reference_kernel(name, rays_per_prim):
-    """BASELINE correctness level 2: per-primitive flux of the oracle against the
-    reference CPU tracer at equal ray counts -- relative L2 of the means and the
-    per-primitive 3-sigma test over K = 8 seeded repeats per side."""
+@pytest.mark.parametrize("name", ["disk3D", "trench", "holes"])
+def test_fixed_ray_set_against_reference_intersector(name):
+    """BASELINE correctness level 1 on the oracle side: geomID / primID / t of the same 200k
+    primary rays + one bounce that tests/test_gpu_parity.py feeds to the CUDA kernels, here
+    against the reference's own Boundary + GeometryDisk + rtcIntersect1 call sequence
+    (rayTraceKernel.hpp:41-45,156-166) in oracle/_ref.  IDs exact, t 0 ulp."""
     if not po.have_ref():
-        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+        pytest.skip("oracle/_ref not built")
     c = common.case(name)
     s = common.make_oracle(c)
-    K = 8
-    num = s.n * rays_per_prim
-    fo, io = _repeat_oracle(s, common.oracle_particle(c), num, [100 + k for k in range(K)])
-    if c["geo"] == "disk":
-        fr, ir, _ = po.ref_trace_disk(c["D"], c["points"], c["normals"], c["grid_delta"], c["bc"],
-                                      c["source_dir"], c["kind"], c["sticking"], c["power"],
-                                      c["cone"], rays_fixed=num, seed=555, runs=K)
-    else:
-        fr, ir, _ = po.ref_trace_triangle(c["verts"], c["tris"], c["grid_delta"], c["bc"],
-                                          c["source_dir"], c["kind"], c["sticking"], c["power"],
-                                          c["cone"], rays_fixed=num, seed=555, runs=K)
+    r = host.disk_radius(c["grid_delta"], c["D"])
+    rays = s.source_rays(common.oracle_particle(c), s.config(10**7, 12346), 0, 200000)
+    for leg in range(2):
+        go, po_, to, ngo = s.intersect(rays)
+        gr, pr, tr, ngr = po.ref_intersect_disks(c["points"], c["normals"], r, s.bbox(),
+                                                 c["source_dir"], rays)
+        assert (go == gr).all(), "geomID mismatch on %d rays" % int((go != gr).sum())
+        assert (po_ == pr).all(), "primID mismatch on %d rays" % int((po_ != pr).sum())
+        hit = go != 0xFFFFFFFF
+        assert hit.mean() > (0.5 if leg == 0 else 0.1)
+        assert (to[hit].view(np.uint32) == tr[hit].view(np.uint32)).all()
+        bnd = go == 0  # unnormalised boundary normals steer processHit (rayBoundary.hpp:36-38)
+        assert (ngo[bnd].view(np.uint32) == ngr[bnd].view(np.uint32)).all()
+        keep = go == 1
+        rays = _first_bounce(s, rays[keep], po_[keep], to[keep], c["D"])
+
+
+def _stat_compare(fo, io, fr, ir, num, K, hits=True):
     mo, mr = fo.mean(0), fr.astype(np.float64).mean(0)
     rel_l2 = np.linalg.norm(mo - mr) / np.linalg.norm(mr)
     # expected L2 of pure sampling noise between two K-run means
@@ -303,8 +321,124 @@ def test_flux_statistical_parity_with_reference_kernel(name, rays_per_prim):
     assert (z > 3).mean() < 0.03, float((z > 3).mean())
     # the random walk has the same shape: traces and hits per ray
     tr_o, tr_r = io.totalTraces / num, ir[1] / num
-    assert abs(tr_o - tr_r) / tr_r < 0.01
-    assert abs(io.geoHits / num - ir[3] / num) / (ir[3] / num) < 0.01
+    assert abs(tr_o - tr_r) / tr_r < 0.01, (tr_o, tr_r)
+    if hits:
+        assert abs(io.geoHits / num - ir[3] / num) / (ir[3] / num) < 0.01
+
+
+def _stat_case(name):
+    """name[+specular][+tilted]: a config of tests/common.py, optionally with the specular
+    particle (rayParticle.hpp:165-204) and a tilted source (raySourceRandom.hpp:88-116)."""
+    parts = name.split("+")
+    c = dict(common.case(parts[0]))
+    primary = None
+    if "specular" in parts:
+        c.update(kind=1, sticking=0.3, power=5.0, cone=0.0)
+    if "tilted" in parts:
+        primary = np.array([0.3, 0.1, -1.0]) / np.linalg.norm([0.3, 0.1, -1.0])
+    return c, primary
+
+
+STAT_CASES = [("disk3D", 50), ("triangle3D", 100), ("disk2D", 2000), ("trench_ion", 60),
+              ("trench", 60), ("holes", 40), ("trench+specular+tilted", 60),
+              ("trench+tilted", 60)]
+
+
+@pytest.mark.parametrize("name,rays_per_prim", STAT_CASES)
+def test_flux_statistical_parity_with_reference_kernel(name, rays_per_prim):
+    """BASELINE correctness level 2: per-primitive flux of the oracle against the
+    reference CPU tracer at equal ray counts -- relative L2 of the means and the
+    per-primitive 3-sigma test over K = 8 seeded repeats per side.  Covers all five
+    configs (C4 with both of its particles, C5 reduced) plus the specular particle and the
+    tilted source."""
+    if not po.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    c, primary = _stat_case(name)
+    s = common.make_oracle(c)
+    K = 8
+    num = s.n * rays_per_prim
+    fo, io = [], None
+    for k in range(K):
+        f, io = s.trace(common.oracle_particle(c), s.config(num, 100 + k, primary_dir=primary))
+        fo.append(f / po.FLUX_SCALE)
+    fo = np.asarray(fo)
+    if c["geo"] == "disk":
+        fr, ir, _ = po.ref_trace_disk(c["D"], c["points"], c["normals"], c["grid_delta"], c["bc"],
+                                      c["source_dir"], c["kind"], c["sticking"], c["power"],
+                                      c["cone"], rays_fixed=num, seed=555, runs=K,
+                                      primary_dir=primary)
+    else:
+        fr, ir, _ = po.ref_trace_triangle(c["verts"], c["tris"], c["grid_delta"], c["bc"],
+                                          c["source_dir"], c["kind"], c["sticking"], c["power"],
+                                          c["cone"], rays_fixed=num, seed=555, runs=K)
+    _stat_compare(fo, io, fr, ir, num, K)
+
+
+def _material_ids(c):
+    """two materials: 'mask' on top (id 1), 'substrate' below the top surface (id 0)"""
+    z = c["points"][:, 2 if c["D"] == 3 else 1]
+    return (z > z.max() - 1e-3).astype(np.int32)
+
+
+OPTION_CASES = [
+    # name, rays/prim, wdist, mean free path, sticking by material
+    ("trench", 60, True, 0.0, None),          # VIENNARAY_USE_WDIST, rayTraceKernel.hpp:258-296
+    ("trench", 60, False, 30.0, None),        # getMeanFreePath() > 0, rayTraceKernel.hpp:179-203
+    ("trench_ion", 60, False, 30.0, None),
+    ("trench", 60, False, 0.0, (0.05, 0.6)),  # materialId-dependent sticking, :310-313
+    ("triangle3D", 40, False, 0.0, (0.02, 0.5)),
+    ("disk3D", 20, True, 25.0, (0.3, 0.05)),  # all three at once
+]
+
+
+@pytest.mark.parametrize("name,rays_per_prim,wdist,mfp,table", OPTION_CASES)
+def test_optional_features_statistical_parity_with_reference(name, rays_per_prim, wdist, mfp,
+                                                             table):
+    """The oracle's restatement of the optional parts of the loop -- distance-weighted spread,
+    mean-free-path scattering, sticking looked up by the hit primitive's materialId -- against
+    the reference's own code: oracle/_ref built a second time with -DVIENNARAY_USE_WDIST, and a
+    user-side particle in oracle/ref_driver.cpp that overrides getMeanFreePath() and switches
+    on the materialId it is handed."""
+    if not po.have_ref() or (wdist and not po.have_ref_wdist()):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    c = common.case(name)
+    s = common.make_oracle(c)
+    mats = None
+    part = common.oracle_particle(c)
+    part.meanFreePath = mfp
+    if table is not None:
+        if c["geo"] == "disk":
+            mats = _material_ids(c)
+        else:  # triangles: by the height of the first vertex
+            z = c["verts"][c["tris"][:, 0], 2]
+            mats = (z > z.max() - 1e-3).astype(np.int32)
+        assert 0 < mats.sum() < len(mats)
+        s.set_material_ids(mats)
+        part.set_sticking_by_material(table)
+    K = 8
+    num = s.n * rays_per_prim
+    fo, io = [], None
+    for k in range(K):
+        f, io = s.trace(part, s.config(num, 300 + k, wdist=wdist))
+        fo.append(f / po.FLUX_SCALE)
+    fo = np.asarray(fo)
+    kw = dict(rays_fixed=num, seed=777, runs=K, mean_free_path=mfp, sticking_by_material=table,
+              material_ids=mats)
+    if c["geo"] == "disk":
+        fr, ir, _ = po.ref_trace_disk(c["D"], c["points"], c["normals"], c["grid_delta"], c["bc"],
+                                      c["source_dir"], c["kind"], c["sticking"], c["power"],
+                                      c["cone"], wdist=wdist, **kw)
+    else:
+        fr, ir, _ = po.ref_trace_triangle(c["verts"], c["tris"], c["grid_delta"], c["bc"],
+                                          c["source_dir"], c["kind"], c["sticking"], c["power"],
+                                          c["cone"], **kw)
+    _stat_compare(fo, io, fr, ir, num, K)
+    if mfp > 0:  # scatter events per ray (TraceInfo.particleHits, rayTraceKernel.hpp:198)
+        assert ir[4] > 0
+        assert abs(io.particleHits - ir[4]) / ir[4] < 0.02, (io.particleHits, int(ir[4]))
+    if table is not None:  # the table is really in use: a constant-sticking run differs
+        f0, _ = s.trace(common.oracle_particle(c), s.config(num, 300))
+        assert not np.allclose(f0 / po.FLUX_SCALE, fo[0])
 
 
 # --------------------------------------------------------------------------------------

@@ -66,6 +66,7 @@ struct vr_ctx {
   float skySign = 0.f, skyTop = 0.f;
   uint32_t tailRays = 262144;  // VR_TAIL_RAYS: survivors handed to the one-launch tail kernel
   int skyCells = 128;  // VR_SKY_CELLS; 0 disables the map
+  bool dumpLaunches = false;  // VR_DUMP_LAUNCHES=1: one line per wavefront iteration (debug)
   bool timeKernels = false;  // VR_TIME_KERNELS=1: CUDA events around every launch
   std::vector<cudaEvent_t> tev;
   std::vector<int> tevKind;
@@ -280,6 +281,8 @@ int vr_ctx_create(int cudaDevice, vr_ctx **out) {
     ctx->spreadMode = ss[0] == '1' ? 1 : 0;
   const char *tk = getenv("VR_TIME_KERNELS");
   ctx->timeKernels = tk && tk[0] == '1';
+  if (const char *dl = getenv("VR_DUMP_LAUNCHES"))
+    ctx->dumpLaunches = dl[0] == '1';
   if (const char *ps = getenv("VR_POOL_SLOTS")) {
     long v = atol(ps);
     if (v >= 1024 && v <= (1l << 26))
@@ -659,6 +662,8 @@ int vr_scene_commit(vr_ctx *ctx) {
   s.nodes = ctx->bvh.nodes;
   s.nodes4 = ctx->bvh.nodes4;
   s.rootRef = ctx->bvh.rootRef;
+  s.top = ctx->bvh.top;
+  s.topCount = ctx->bvh.topCount;
   s.sky = nullptr;  // rebuilt by the next trace
   ctx->committed = true;
   return VR_OK;
@@ -819,6 +824,13 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
         batch = (int)std::min<uint64_t>(std::max<uint64_t>((shardRays - handed) / slots, 1), 256);
       else if (compacted)
         batch = bound > 262144u ? 2 : (bound > 8192u ? 16 : 64);  // the long thin tail
+      cudaEvent_t dumpEv[3] = {nullptr, nullptr, nullptr};
+      if (ctx->dumpLaunches) {
+        batch = 1;
+        for (auto &e : dumpEv)
+          cudaEventCreate(&e);
+        cudaEventRecord(dumpEv[0], ctx->stream);
+      }
       for (int b = 0; b < batch; ++b) {
         p.pool = cur ? ctx->pool2 : ctx->pool;
         p.poolOut = cur ? ctx->pool : ctx->pool2;
@@ -827,6 +839,8 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
         mark(ctx, 2);
         CK(launchTraverse(p, ctx->numSMs, ctx->stream));
         mark(ctx, 0);
+        if (dumpEv[1])
+          cudaEventRecord(dumpEv[1], ctx->stream);
         CK(launchShade(p, ctx->stream));
         CK(launchSpread(p, ctx->numSMs, ctx->stream));
         mark(ctx, 1);
@@ -844,11 +858,22 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
           compacted = true;
         }
       }
+      if (dumpEv[2])
+        cudaEventRecord(dumpEv[2], ctx->stream);
       CK(cudaEventRecord(ctx->liveEv[0], ctx->stream));
       CK(cudaEventSynchronize(ctx->liveEv[0]));
       const uint32_t live = ctx->hLive[0];
       unsigned long long cursor;
       memcpy(&cursor, &ctx->hLive[2], sizeof(cursor));
+      if (dumpEv[2]) {
+        float tms = 0.f, sms = 0.f;
+        cudaEventElapsedTime(&tms, dumpEv[0], dumpEv[1]);
+        cudaEventElapsedTime(&sms, dumpEv[1], dumpEv[2]);
+        fprintf(stderr, "[vr] particle %d iter %d slots %u compact %d live %u handed %llu traverse %.4f ms shade+flip %.4f ms\n",
+                k, ctx->iterations, compacted ? bound : slots, (int)compact, live, cursor, tms, sms);
+        for (auto &e : dumpEv)
+          cudaEventDestroy(e);
+      }
       handed = std::min<uint64_t>(cursor, shardRays);
       if (live == 0u)
         break;
@@ -903,6 +928,7 @@ static int downloadFixed(vr_ctx *ctx, std::vector<unsigned long long> &flux,
   if (!ctx->dResult)
     return fail(ctx, VR_ERR_STATE, "download: no trace has run");
   CK(cudaSetDevice(ctx->device));
+
   const size_t n = ctx->n, np = ctx->numParticles;
   for (size_t k = 0; k < np; ++k)
     CK(launchUnsortFlux(ctx->dResult + k * n, ctx->bvh.sortedToOrig, (uint32_t)n,

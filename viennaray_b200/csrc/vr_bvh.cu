@@ -7,12 +7,25 @@
 //      internal node; index bits break ties between equal codes
 //   4. bottom-up refit of node boxes with one atomic flag per node
 //   5. emission of 32-byte nodes holding both child boxes on a 16-bit grid; subtrees of at
-//      most VR_LEAF_MAX primitives become leaves (contiguous sorted ranges)
+//      most VR_LEAF_MAX primitives become leaves (contiguous sorted ranges).  Only about
+//      one radix-tree node in seven survives the leaf collapse, so the survivors are
+//      renumbered densely by a prefix sum over the radix-tree order: a subtree's nodes stay
+//      contiguous (every internal node of a subtree lies inside its key range), the node
+//      array shrinks from 32 B x (n-1) to 32 B x numNodes and a 128-byte cache line holds
+//      four nodes that are visited together instead of one
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "vr_internal.h"
+
+// entries of the top-of-tree table the traverse kernel keeps in shared memory (0: none);
+// VR_TOP_NODES in the environment overrides it
+#ifndef VR_TOP_DEFAULT
+#define VR_TOP_DEFAULT 0u
+#endif
 
 namespace vr {
 
@@ -140,6 +153,33 @@ __device__ __forceinline__ uint32_t childRef(int first, int last, int internalId
   return (uint32_t)internalIdx;
 }
 
+// depth of the radix tree: every primitive climbs to the root and counts the levels above
+// it (the emitted tree is never deeper: collapsing subtrees into leaves only removes levels)
+__global__ void depthKernel(const int *parentOfInternal, const int *parentOfLeaf, int n,
+                            unsigned int *maxDepth) {
+  int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned d = 0;
+  if (leaf < n)
+    for (int node = parentOfLeaf[leaf]; node >= 0; node = parentOfInternal[node])
+      ++d;
+  d = __reduce_max_sync(0xffffffffu, d);
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(maxDepth, d);
+}
+
+// radix-tree node i survives the leaf collapse (is referenced by the emitted tree)
+__global__ void liveKernel(const int2 *range, int n, uint32_t leafMax, uint32_t *live) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+  const int2 r = range[i];
+  live[i] = ((uint32_t)(r.y - r.x + 1) > leafMax || i == 0) ? 1u : 0u;
+}
+// reference of the radix tree -> reference of the dense node array
+__device__ __forceinline__ uint32_t denseRef(uint32_t ref, const uint32_t *dense) {
+  return (ref & VR_LEAF_FLAG) ? ref : dense[ref];
+}
+
 // box -> six 16-bit grid coordinates, rounded outwards by one extra cell so the
 // decode (a fused multiply-add in the traversal) can never shrink the box
 __device__ __forceinline__ uint4 quantizeChild(float4 l, float4 h, float3 qLo, float3 qInv,
@@ -160,7 +200,8 @@ __device__ __forceinline__ uint4 quantizeChild(float4 l, float4 h, float3 qLo, f
 __device__ __forceinline__ void emitNode(int i, const float4 *lo, const float4 *hi,
                                          const uint32_t *sorted, int n, const int2 *range,
                                          const int *split, const float4 *nodeLo,
-                                         const float4 *nodeHi, Node2 *nodes, float3 qLo,
+                                         const float4 *nodeHi, const uint32_t *dense,
+                                         Node2 *nodes, float3 qLo,
                                          float3 qInv, double *sah, double &aIn, double &aLeaf,
                                          unsigned &cNodes, unsigned &cLeaves,
                                          unsigned &cMaxLeaf, uint32_t leafMax) {
@@ -195,9 +236,9 @@ __device__ __forceinline__ void emitNode(int i, const float4 *lo, const float4 *
     ref1 = childRef(rc.x, rc.y, g + 1, leafMax);
   }
   Node2 nd;
-  nd.c0 = quantizeChild(l0, h0, qLo, qInv, ref0);
-  nd.c1 = quantizeChild(l1, h1, qLo, qInv, ref1);
-  nodes[i] = nd;
+  nd.c0 = quantizeChild(l0, h0, qLo, qInv, denseRef(ref0, dense));
+  nd.c1 = quantizeChild(l1, h1, qLo, qInv, denseRef(ref1, dense));
+  nodes[dense[i]] = nd;
   cNodes = 1u;
   cLeaves = ((ref0 & VR_LEAF_FLAG) ? 1u : 0u) + ((ref1 & VR_LEAF_FLAG) ? 1u : 0u);
   if (ref0 & VR_LEAF_FLAG)
@@ -223,12 +264,13 @@ __device__ __forceinline__ void emitNode(int i, const float4 *lo, const float4 *
 
 __global__ void emitKernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
                            const int2 *range, const int *split, const float4 *nodeLo,
-                           const float4 *nodeHi, Node2 *nodes, unsigned int *stats, float3 qLo,
-                           float3 qInv, double *sah, uint32_t leafMax) {
+                           const float4 *nodeHi, const uint32_t *dense, Node2 *nodes,
+                           unsigned int *stats, float3 qLo, float3 qInv, double *sah,
+                           uint32_t leafMax) {
   double aIn = 0., aLeaf = 0.;
   unsigned cNodes = 0u, cLeaves = 0u, cMaxLeaf = 0u;
   emitNode(blockIdx.x * blockDim.x + threadIdx.x, lo, hi, sorted, n, range, split, nodeLo, nodeHi,
-           nodes, qLo, qInv, sah, aIn, aLeaf, cNodes, cLeaves, cMaxLeaf, leafMax);
+           dense, nodes, qLo, qInv, sah, aIn, aLeaf, cNodes, cLeaves, cMaxLeaf, leafMax);
   // statistics and SAH terms summed per warp first: a million atomics on one address
   // serialise
   cNodes = __reduce_add_sync(0xffffffffu, cNodes);
@@ -283,8 +325,8 @@ __device__ __forceinline__ ChildBox childOf(int i, int side, const float4 *lo, c
 
 __global__ void emit4Kernel(const float4 *lo, const float4 *hi, const uint32_t *sorted, int n,
                             const int2 *range, const int *split, const float4 *nodeLo,
-                            const float4 *nodeHi, uint4 *nodes4, float3 qLo, float3 qInv,
-                            uint32_t leafMax) {
+                            const float4 *nodeHi, const uint32_t *dense, uint4 *nodes4,
+                            float3 qLo, float3 qInv, uint32_t leafMax) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1)
     return;
@@ -296,19 +338,61 @@ __global__ void emit4Kernel(const float4 *lo, const float4 *hi, const uint32_t *
   for (int side = 0; side < 2; ++side) {
     const ChildBox b = childOf(i, side, lo, hi, sorted, range, split, nodeLo, nodeHi, leafMax);
     if (b.ref & VR_LEAF_FLAG) {
-      e[k++] = quantizeChild(b.lo, b.hi, qLo, qInv, b.ref);
+      e[k++] = quantizeChild(b.lo, b.hi, qLo, qInv, b.ref);  // a leaf reference
     } else {
       for (int s2 = 0; s2 < 2; ++s2) {
         const ChildBox g =
             childOf((int)b.ref, s2, lo, hi, sorted, range, split, nodeLo, nodeHi, leafMax);
-        e[k++] = quantizeChild(g.lo, g.hi, qLo, qInv, g.ref);
+        e[k++] = quantizeChild(g.lo, g.hi, qLo, qInv, denseRef(g.ref, dense));
       }
     }
   }
   for (; k < 4; ++k)
     e[k] = make_uint4(0u, 0u, 0u, VR_DONE);
   for (k = 0; k < 4; ++k)
-    nodes4[4 * (size_t)i + k] = e[k];
+    nodes4[4 * (size_t)dense[i] + k] = e[k];
+}
+
+// Top of the tree in breadth-first order for the traverse kernel's shared-memory copy.
+// One block walks the levels; a child that still fits the table gets the reference
+// VR_TOP_BASE + entry, every other reference is kept as it is.
+__global__ void topTableKernel(const Node2 *nodes, uint32_t maxTop, uint4 *top,
+                               uint32_t *countOut) {
+  __shared__ uint32_t ids[VR_TOP_MAX];
+  __shared__ uint32_t count;
+  if (threadIdx.x == 0) {
+    ids[0] = 0u;
+    count = 1u;
+  }
+  __syncthreads();
+  uint32_t b = 0, e = 1;
+  while (b < e) {
+    for (uint32_t k = b + threadIdx.x; k < e; k += blockDim.x) {
+      Node2 nd = nodes[ids[k]];
+      if (nd.c0.w < VR_DONE) {
+        const uint32_t pos = atomicAdd(&count, 1u);
+        if (pos < maxTop) {
+          ids[pos] = nd.c0.w;
+          nd.c0.w = VR_TOP_BASE + pos;
+        }
+      }
+      if (nd.c1.w < VR_DONE) {
+        const uint32_t pos = atomicAdd(&count, 1u);
+        if (pos < maxTop) {
+          ids[pos] = nd.c1.w;
+          nd.c1.w = VR_TOP_BASE + pos;
+        }
+      }
+      top[2 * k] = nd.c0;
+      top[2 * k + 1] = nd.c1;
+    }
+    __syncthreads();
+    b = e;
+    e = min(count, maxTop);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *countOut = e;
 }
 
 }  // namespace
@@ -327,7 +411,7 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
                             const float sceneLo[3], const float sceneHi[3], float3 sInv,
                             uint32_t leafMax, cudaStream_t stream, Bvh *out) {
   freeBvh(out, stream);
-  const bool wide = getenv("VR_BVH_WIDE") && atoi(getenv("VR_BVH_WIDE")) > 0;
+  bool wide = getenv("VR_BVH_WIDE") && atoi(getenv("VR_BVH_WIDE")) > 0;
   unsigned long long *keys = nullptr, *keysSorted = nullptr;
   uint32_t *vals = nullptr;
   void *tmp = nullptr;
@@ -335,9 +419,14 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
   int *split = nullptr, *parI = nullptr, *parL = nullptr, *flags = nullptr;
   float4 *nodeLo = nullptr, *nodeHi = nullptr;
   unsigned int *stats = nullptr;
+  uint32_t *live = nullptr, *dense = nullptr;
+  void *scanTmp = nullptr;
   double *sah = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   auto cleanup = [&]() {
+    cudaFreeAsync(live, stream);
+    cudaFreeAsync(dense, stream);
+    cudaFreeAsync(scanTmp, stream);
     cudaFreeAsync(keys, stream);
     cudaFreeAsync(keysSorted, stream);
     cudaFreeAsync(vals, stream);
@@ -407,10 +496,11 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
     VR_CK(cudaMallocAsync(&flags, sizeof(int) * (n - 1), stream));
     VR_CK(cudaMallocAsync(&nodeLo, sizeof(float4) * (n - 1), stream));
     VR_CK(cudaMallocAsync(&nodeHi, sizeof(float4) * (n - 1), stream));
-    VR_CK(cudaMallocAsync(&stats, sizeof(unsigned int) * 4, stream));
-    VR_CK(cudaMallocAsync(&out->nodes, sizeof(Node2) * (n - 1), stream));
+    VR_CK(cudaMallocAsync(&stats, sizeof(unsigned int) * 8, stream));
+    VR_CK(cudaMallocAsync(&live, sizeof(uint32_t) * (n - 1), stream));
+    VR_CK(cudaMallocAsync(&dense, sizeof(uint32_t) * (n - 1), stream));
     VR_CK(cudaMemsetAsync(flags, 0, sizeof(int) * (n - 1), stream));
-    VR_CK(cudaMemsetAsync(stats, 0, sizeof(unsigned int) * 4, stream));
+    VR_CK(cudaMemsetAsync(stats, 0, sizeof(unsigned int) * 8, stream));
     VR_CK(cudaMallocAsync(&sah, sizeof(double) * 4, stream));
     VR_CK(cudaMemsetAsync(sah, 0, sizeof(double) * 4, stream));
     radixTreeKernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(keysSorted, (int)n, range, split, parI,
@@ -419,18 +509,53 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
     refitKernel<<<(n + B - 1) / B, B, 0, stream>>>(primLo, primHi, out->sortedToOrig, (int)n,
                                                    range, split, parI, parL, nodeLo, nodeHi, flags);
     VR_CK(cudaGetLastError());
+    depthKernel<<<(n + B - 1) / B, B, 0, stream>>>(parI, parL, (int)n, stats + 4);
+    VR_CK(cudaGetLastError());
+    // dense numbering of the nodes that survive the leaf collapse (radix-tree order kept)
+    liveKernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(range, (int)n, leafMax, live);
+    VR_CK(cudaGetLastError());
+    size_t scanBytes = 0;
+    VR_CK(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, live, dense, (int)(n - 1), stream));
+    VR_CK(cudaMallocAsync(&scanTmp, scanBytes ? scanBytes : 16, stream));
+    VR_CK(cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, live, dense, (int)(n - 1), stream));
+    uint32_t lastDense = 0, lastLive = 0, depth = 0;
+    VR_CK(cudaMemcpyAsync(&depth, stats + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    VR_CK(cudaMemcpyAsync(&lastDense, dense + (n - 2), sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          stream));
+    VR_CK(cudaMemcpyAsync(&lastLive, live + (n - 2), sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          stream));
+    VR_CK(cudaStreamSynchronize(stream));
+    const size_t numLive = (size_t)lastDense + lastLive;
+    out->maxDepth = depth;
+    // The traversal stacks are unchecked (VR_STACK entries).  Binary descent: one push per
+    // level at most.  4-wide descent: three per node, a node spanning two binary levels.
+    if (depth > VR_STACK) {
+      cleanup();
+      return cudaErrorInvalidConfiguration;  // cannot happen for 63 + 32 key bits
+    }
+    if (wide && 3u * ((depth + 1u) / 2u) > VR_STACK)
+      wide = false;  // too deep for the wide traversal's stack: binary nodes only
+    VR_CK(cudaMallocAsync(&out->nodes, sizeof(Node2) * std::max<size_t>(numLive, 1), stream));
     emitKernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(primLo, primHi, out->sortedToOrig, (int)n,
-                                                      range, split, nodeLo, nodeHi, out->nodes,
-                                                      stats, qLo, qInv, sah, leafMax);
+                                                      range, split, nodeLo, nodeHi, dense,
+                                                      out->nodes, stats, qLo, qInv, sah, leafMax);
     VR_CK(cudaGetLastError());
     if (wide) {
-      VR_CK(cudaMallocAsync(&out->nodes4, sizeof(uint4) * 4 * (size_t)(n - 1), stream));
+      VR_CK(cudaMallocAsync(&out->nodes4, sizeof(uint4) * 4 * std::max<size_t>(numLive, 1), stream));
       emit4Kernel<<<(n - 1 + B - 1) / B, B, 0, stream>>>(primLo, primHi, out->sortedToOrig, (int)n,
-                                                         range, split, nodeLo, nodeHi,
+                                                         range, split, nodeLo, nodeHi, dense,
                                                          out->nodes4, qLo, qInv, leafMax);
       VR_CK(cudaGetLastError());
     }
-    unsigned int hs[4];
+    uint32_t topWanted = VR_TOP_DEFAULT;
+    if (const char *tn = getenv("VR_TOP_NODES"))
+      topWanted = (uint32_t)std::min<long>(std::max<long>(atol(tn), 0), (long)VR_TOP_MAX);
+    if (topWanted && !wide) {
+      VR_CK(cudaMallocAsync(&out->top, sizeof(uint4) * 2 * topWanted, stream));
+      topTableKernel<<<1, 256, 0, stream>>>(out->nodes, topWanted, out->top, stats + 3);
+      VR_CK(cudaGetLastError());
+    }
+    unsigned int hs[8];
     double hsah[4];
     VR_CK(cudaMemcpyAsync(hs, stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
     VR_CK(cudaMemcpyAsync(hsah, sah, sizeof(hsah), cudaMemcpyDeviceToHost, stream));
@@ -440,6 +565,7 @@ static cudaError_t buildOne(const float4 *primLo, const float4 *primHi, uint32_t
     out->numNodes = hs[0];
     out->numLeaves = hs[1];
     out->maxLeaf = hs[2];
+    out->topCount = out->top ? hs[3] : 0u;
     out->rootRef = 0u;
   }
   VR_CK(cudaEventRecord(e1, stream));
@@ -521,6 +647,7 @@ cudaError_t buildBvh(const float4 *primLo, const float4 *primHi, uint32_t n, con
 void freeBvh(Bvh *b, cudaStream_t stream) {
   cudaFreeAsync(b->nodes, stream);
   cudaFreeAsync(b->nodes4, stream);
+  cudaFreeAsync(b->top, stream);
   cudaFreeAsync(b->sortedToOrig, stream);
   *b = Bvh();
 }

@@ -250,8 +250,27 @@ __device__ __forceinline__ bool better(float t, uint32_t geom, uint32_t orig, co
 
 // oriented disc: den = dot(dir,n); t = dot(c-org,n)/den; tnear <= t;
 // |org + dir t - c|^2 < r^2 (Embree DiscIntersector1, oriented variant).
+#ifndef VR_DISK_FMA
+#define VR_DISK_FMA 0
+#endif
 __device__ __forceinline__ void testDisk(const float4 P, const float4 N, uint32_t prim,
                                          const V3 &org, const V3 &dir, Hit &best) {
+#if VR_DISK_FMA
+  // fused formulation (timing experiment; the oracle would have to follow)
+  float den = __fmaf_rn(dir.z, N.z, __fmaf_rn(dir.y, N.y, dir.x * N.x));
+  if (den == 0.f)
+    return;
+  const float num = __fmaf_rn(P.z - org.z, N.z, __fmaf_rn(P.y - org.y, N.y, (P.x - org.x) * N.x));
+  if (num == 0.f)
+    return;
+  float t = num / den;
+  if (!(VR_TNEAR <= t && t <= 3.402823466e+38f))
+    return;
+  float qx = __fmaf_rn(dir.x, t, org.x) - P.x, qy = __fmaf_rn(dir.y, t, org.y) - P.y,
+        qz = __fmaf_rn(dir.z, t, org.z) - P.z;
+  if (!(__fmaf_rn(qz, qz, __fmaf_rn(qy, qy, qx * qx)) < P.w * P.w))
+    return;
+#else
   float den = dot3(dir.x, dir.y, dir.z, N.x, N.y, N.z);
   if (den == 0.f)
     return;
@@ -268,6 +287,7 @@ __device__ __forceinline__ void testDisk(const float4 P, const float4 N, uint32_
         qz = (org.z + dir.z * t) - P.z;
   if (!(dot3(qx, qy, qz, qx, qy, qz) < P.w * P.w))
     return;
+#endif
   uint32_t orig = __float_as_uint(N.w);
   if (better(t, 1u, orig, best)) {
     best.t = t;
@@ -328,8 +348,18 @@ __device__ __forceinline__ bool checkLocal(const float4 P, const float4 N, const
     return false;
   float hx = (org.x + dir.x * tt) - P.x, hy = (org.y + dir.y * tt) - P.y,
         hz = (org.z + dir.z * tt) - P.z;
-  float distance = sqrtf(dot3(hx, hy, hz, hx, hy, hz));
-  return P.w > distance;
+  // radius > sqrtf(d2), decided without the square root unless d2 lies within 1e-5 of r^2
+  // (relative): d2 < fl(r2 * 0.99999) < r^2 (1 - 9e-6) gives sqrt_rn(d2) < r, and the mirror
+  // image for the other side; a radius whose square leaves the normal range takes the
+  // square root.  Same decision as the reference's comparison in every case.
+  const float d2 = dot3(hx, hy, hz, hx, hy, hz), r2 = P.w * P.w;
+  if (r2 > 1e-30f) {
+    if (d2 < r2 * 0.99999f)
+      return true;
+    if (d2 > r2 * 1.00001f)
+      return false;
+  }
+  return P.w > sqrtf(d2);
 }
 
 // checkLocalIntersection with the impact distance handed out (WDIST)

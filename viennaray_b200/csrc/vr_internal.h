@@ -15,10 +15,16 @@
 #ifndef VR_LEAF_MAX_TRI
 #define VR_LEAF_MAX_TRI 4u
 #endif
+#define VR_STACK 96          // entries of a ray's traversal stack (see vr_trace.cu)
 #define VR_DONE 0x7fffffffu  // traversal finished / unused child (not a valid node index)
 #define VR_LEAF_FLAG 0x80000000u  // child reference: leaf(first << 4 | count)
 #define VR_FIXED_SCALE 1073741824.0f
 #define VR_COUNTER_COPIES 64      // replicated TraceInfo counters (summed on download)
+// References >= VR_TOP_BASE (and < VR_DONE) name an entry of the top-of-tree table that the
+// traverse kernel stages in shared memory (primitive counts stay below 2^27, so real node
+// indices never get here)
+#define VR_TOP_BASE 0x7f000000u
+#define VR_TOP_MAX 4096u          // capacity of the table (entries of 32 bytes)
 
 namespace vr {
 
@@ -44,6 +50,11 @@ struct DeviceScene {
   const Node2 *nodes;
   const uint4 *nodes4;  // optional 4-wide nodes or null
   uint32_t rootRef;
+  // top of the tree in breadth-first order (2 x uint4 per entry like a Node2; child
+  // references inside the table are VR_TOP_BASE + entry); entry 0 is the root.  topCount 0:
+  // no table.
+  const uint4 *top;
+  uint32_t topCount;
   float qLo[3], qScale[3];  // node box coordinate = qLo + q * qScale
   // sky map (vr_scene.cu buildSky): a G x G grid over the two lateral axes; per
   // cell {base, slope}.  A ray that leaves a surface point of the cell towards
@@ -109,12 +120,15 @@ struct TraceParams {
 struct Bvh {
   Node2 *nodes = nullptr;
   uint4 *nodes4 = nullptr;  // optional 4-wide nodes (4 x uint4 each), same indices as `nodes`
+  uint4 *top = nullptr;     // breadth-first top-of-tree table (see DeviceScene::top)
+  uint32_t topCount = 0;
   uint32_t numNodes = 0;
   uint32_t rootRef = 0;
   uint32_t *sortedToOrig = nullptr;  // device, numPrims
   float qLo[3] = {0, 0, 0}, qScale[3] = {1, 1, 1};
   float buildMs = 0.f;
   uint32_t numLeaves = 0, maxLeaf = 0;
+  uint32_t maxDepth = 0;  // levels of the radix tree (upper bound of the emitted tree's)
   float mortonAlpha = 1.f;  // shape of the Morton cells the kept tree was built with
   float sahInner = 0.f, sahLeaf = 0.f;  // SAH terms: sum of inner-node areas, of leaf areas x
                                         // primitive counts, both over the root area

@@ -25,12 +25,12 @@
 
 namespace vr {
 
-// Traversal stack: the radix tree over 63-bit Morton keys, ties broken by the 32-bit index,
-// is at most 63 + 32 levels deep and a binary descent pushes at most one entry per level,
-// so 96 entries cannot overflow (the bounds checks at the pushes are belt and braces; the
-// optional 4-wide variant pushes up to three per level and relies on real trees being far
-// shallower than that bound).
-#define VR_STACK 96
+// Traversal stack.  The pushes carry no bounds check: the build measures the depth of the
+// radix tree (vr_bvh.cu, depthKernel) and refuses a tree a traversal could overflow on.  A
+// binary descent pushes at most one entry per level and the tree over 63-bit Morton keys,
+// ties broken by the 32-bit index, is at most 95 levels deep, so VR_STACK entries always
+// do; the optional 4-wide variant pushes up to three per (double) level and is only
+// emitted when 3 * ceil(depth / 2) fits.
 #ifndef VR_NODE_MIN
 #define VR_NODE_MIN 1  // lanes at inner nodes needed to keep the warp in the node loop
 #endif
@@ -42,6 +42,18 @@ namespace vr {
 #endif
 #ifndef VR_TRAV_BLOCKS_WIDE
 #define VR_TRAV_BLOCKS_WIDE 10  // the same for the 4-wide node variant
+#endif
+// the traverse kernel with the top of the tree in shared memory: fewer, larger blocks share
+// one copy of the table (2 x 640 threads = the 40 warps per SM of 10 x 128)
+#ifndef VR_TRAV_THREADS_TOP
+#define VR_TRAV_THREADS_TOP 640
+#endif
+#ifndef VR_TRAV_BLOCKS_TOP
+#define VR_TRAV_BLOCKS_TOP 2
+#endif
+// entries of the traversal stack kept in shared memory (0: all of it in local memory)
+#ifndef VR_SMEM_STACK
+#define VR_SMEM_STACK 0
 #endif
 #define VR_WDIST_CAP 64  // disks one ray can hit at once (hit disk + its neighbour list)
 #ifndef VR_SHADE_BLOCKS_Q
@@ -179,9 +191,16 @@ __device__ __forceinline__ unsigned long long warpSum(unsigned long long v) {
 // own: t = (2^23 + q) * slope + (offset - 2^23 * slope).  The folded offset is rounded at
 // the magnitude 2^23 * slope, i.e. to half a grid cell; the boxes were widened by a full
 // cell at build time, so the test stays conservative.
+#ifndef VR_HOIST_SEL
+#define VR_HOIST_SEL 0  // 1: keep the far-plane selectors in registers (three more) instead of
+                        // deriving them from the near-plane ones at every node
+#endif
 struct NodeRay {
   float ix, iy, iz, ox, oy, oz;
   uint32_t sx, sy, sz;
+#if VR_HOIST_SEL
+  uint32_t fx, fy, fz;
+#endif
 };
 __device__ __forceinline__ NodeRay makeNodeRay(const DeviceScene &sc, const V3 &org, const V3 &dir) {
   NodeRay r;
@@ -204,17 +223,27 @@ __device__ __forceinline__ NodeRay makeNodeRay(const DeviceScene &sc, const V3 &
   r.sx = r.ix < 0.f ? 0x7632u : 0x7610u;
   r.sy = r.iy < 0.f ? 0x7632u : 0x7610u;
   r.sz = r.iz < 0.f ? 0x7632u : 0x7610u;
+#if VR_HOIST_SEL
+  r.fx = r.sx ^ 0x22u;
+  r.fy = r.sy ^ 0x22u;
+  r.fz = r.sz ^ 0x22u;
+#endif
   return r;
 }
 __device__ __forceinline__ void slabChild(const uint4 c, const NodeRay &r, float tmax, float &n,
                                           float &f) {
   const uint32_t M = 0x4B000000u;
+#if VR_HOIST_SEL
+  const uint32_t qx = r.fx, qy = r.fy, qz = r.fz;
+#else
+  const uint32_t qx = r.sx ^ 0x22u, qy = r.sy ^ 0x22u, qz = r.sz ^ 0x22u;
+#endif
   const float nx = __fmaf_rn(__uint_as_float(__byte_perm(c.x, M, r.sx)), r.ix, r.ox);
-  const float fx = __fmaf_rn(__uint_as_float(__byte_perm(c.x, M, r.sx ^ 0x22u)), r.ix, r.ox);
+  const float fx = __fmaf_rn(__uint_as_float(__byte_perm(c.x, M, qx)), r.ix, r.ox);
   const float ny = __fmaf_rn(__uint_as_float(__byte_perm(c.y, M, r.sy)), r.iy, r.oy);
-  const float fy = __fmaf_rn(__uint_as_float(__byte_perm(c.y, M, r.sy ^ 0x22u)), r.iy, r.oy);
+  const float fy = __fmaf_rn(__uint_as_float(__byte_perm(c.y, M, qy)), r.iy, r.oy);
   const float nz = __fmaf_rn(__uint_as_float(__byte_perm(c.z, M, r.sz)), r.iz, r.oz);
-  const float fz = __fmaf_rn(__uint_as_float(__byte_perm(c.z, M, r.sz ^ 0x22u)), r.iz, r.oz);
+  const float fz = __fmaf_rn(__uint_as_float(__byte_perm(c.z, M, qz)), r.iz, r.oz);
   n = fmaxf(fmaxf(nx, ny), fmaxf(nz, VR_TNEAR));
   f = fminf(fminf(fx, fy), fminf(fz, tmax));
 }
@@ -246,8 +275,7 @@ __device__ __forceinline__ void traverseOne(const DeviceScene &sc, const V3 &org
       const uint32_t r0 = c0.w, r1 = c1.w;
       if (h0 && h1) {
         const bool swap = n1 < n0;
-        if (sp < VR_STACK)
-          stack[sp++] = swap ? r0 : r1;
+        stack[sp++] = swap ? r0 : r1;
         cur = swap ? r1 : r0;
       } else if (h0) {
         cur = r0;
@@ -280,16 +308,82 @@ __device__ __forceinline__ void traverseOne(const DeviceScene &sc, const V3 &org
 // ---------------------------------------------------------------------------
 // traverse: closest hit of every live slot
 // ---------------------------------------------------------------------------
-template <int GEO, int WIDE, int COUNT>
-__global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOCKS) traverseKernel(const __grid_constant__ TraceParams p) {
+// one-dimensional bulk copy global -> shared (TMA, cp.async.bulk) completing on an mbarrier
+__device__ __forceinline__ void bulkLoadTop(uint4 *dst, const uint4 *src, uint32_t bytes,
+                                            unsigned long long *mbar) {
+  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar);
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], "
+                 "%2, [%3];" ::"r"(d),
+                 "l"(src), "r"(bytes), "r"(mb)
+                 : "memory");
+  }
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                 "selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(mb)
+                 : "memory");
+}
+
+template <int TOP> struct TravShape {
+  static constexpr int threads = TOP ? VR_TRAV_THREADS_TOP : 128;
+};
+template <int GEO, int WIDE, int COUNT, int TOP>
+__global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
+                                  TOP ? VR_TRAV_BLOCKS_TOP
+                                      : (WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOCKS))
+    traverseKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned ltMask = (1u << lane) - 1u;
   const uint32_t numSlots = *p.slotCount;
+  constexpr int T = TravShape<TOP>::threads;
+  extern __shared__ __align__(128) uint4 smTop[];  // TOP: the first sc.topCount entries
+#if VR_SMEM_STACK > 0
+  __shared__ uint32_t smStack[VR_SMEM_STACK * T];
+  uint32_t *const sst = smStack + threadIdx.x;
+#endif
+  if (TOP) {
+    __shared__ unsigned long long mbar;
+    bulkLoadTop(smTop, sc.top, sc.topCount * 32u, &mbar);
+  }
+#if VR_SMEM_STACK > 0
+#define VR_PUSH(v)                                                                                 \
+  {                                                                                                \
+    if (sp < VR_SMEM_STACK)                                                                        \
+      sst[sp * T] = (v);                                                                           \
+    else                                                                                           \
+      stack[sp - VR_SMEM_STACK] = (v);                                                             \
+    ++sp;                                                                                          \
+  }
+#define VR_POP(dst)                                                                                \
+  {                                                                                                \
+    --sp;                                                                                          \
+    dst = sp < VR_SMEM_STACK ? sst[sp * T] : stack[sp - VR_SMEM_STACK];                            \
+  }
+#else
+#define VR_PUSH(v)                                                                                 \
+  {                                                                                                \
+    stack[sp] = (v);                                                                               \
+    ++sp;                                                                                          \
+  }
+#define VR_POP(dst)                                                                                \
+  { dst = stack[--sp]; }
+#endif
 
   uint32_t slot = VR_INVALID_ID;
   V3 org = {0.f, 0.f, 0.f}, dir = {0.f, 0.f, 1.f};
-  NodeRay nr = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0x7610u, 0x7610u, 0x7610u};
+  NodeRay nr = makeNodeRay(sc, org, dir);
   Hit best;
   best.t = 0.f;
   best.geom = best.prim = best.orig = VR_INVALID_ID;
@@ -327,7 +421,7 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
             best.prim = best.orig = __float_as_uint(h0.y);
             best.geom = __float_as_uint(h0.z);
             sp = 0;
-            cur = sc.numPrims ? sc.rootRef : VR_DONE;
+            cur = sc.numPrims ? (TOP ? VR_TOP_BASE : sc.rootRef) : VR_DONE;
           }
         }
       }
@@ -391,22 +485,26 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
         if (count == 0) {
           cur = VR_DONE;
           if (sp)
-            cur = stack[--sp];
+            VR_POP(cur)
         } else {
           cur = ref[0];
-          if (sp + 3 <= VR_STACK) {
-            if (count > 3)
-              stack[sp++] = ref[3];
-            if (count > 2)
-              stack[sp++] = ref[2];
-            if (count > 1)
-              stack[sp++] = ref[1];
-          }
+          if (count > 3)
+            VR_PUSH(ref[3])
+          if (count > 2)
+            VR_PUSH(ref[2])
+          if (count > 1)
+            VR_PUSH(ref[1])
         }
       }
       if (!WIDE && atNode) {
         uint4 c0, c1;
-        ldg256(sc.nodes + cur, c0, c1);
+        if (TOP && cur >= VR_TOP_BASE) {
+          const uint4 *q = smTop + 2u * (cur - VR_TOP_BASE);
+          c0 = q[0];
+          c1 = q[1];
+        } else {
+          ldg256(sc.nodes + cur, c0, c1);
+        }
         if (COUNT)
           ++wNodes;
         // slab tests with an explicit FMA per plane (slabChild); the boxes were
@@ -419,16 +517,14 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
         const bool h1 = n1 <= __fmaf_rn(f1, 1.00003f, 2e-6f);
         const uint32_t r0 = c0.w, r1 = c1.w;
         const bool swap = n1 < n0;
-        if (h0 && h1 && sp < VR_STACK) {
-          stack[sp] = swap ? r0 : r1;
-          ++sp;
-        }
+        if (h0 && h1)
+          VR_PUSH(swap ? r0 : r1)
         if (h0 || h1) {
           cur = (h0 && (!h1 || !swap)) ? r0 : r1;
         } else {
           cur = VR_DONE;
           if (sp)
-            cur = stack[--sp];
+            VR_POP(cur)
         }
       }
     }
@@ -438,7 +534,7 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
       const uint32_t first = (cur & 0x7fffffffu) >> 4, count = cur & 15u;
       cur = VR_DONE;
       if (sp)
-        cur = stack[--sp];
+        VR_POP(cur)
       for (uint32_t k = 0; k < count; ++k) {
         const uint32_t i = first + k;
         if (GEO == 0) {
@@ -464,6 +560,8 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
     }
   }
 
+#undef VR_PUSH
+#undef VR_POP
   if (COUNT && p.work) {
     unsigned long long a = warpSum((unsigned long long)wNodes),
                        b = warpSum((unsigned long long)wPrims);
@@ -474,22 +572,33 @@ __global__ void __launch_bounds__(128, WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOC
   }
 }
 
-template <int GEO, int WIDE, int COUNT>
+template <int GEO, int WIDE, int COUNT, int TOP>
 static cudaError_t launchTraverseT(const TraceParams &p, int numSMs, cudaStream_t s) {
+  constexpr int T = TravShape<TOP>::threads;
+  // the table is sized per scene; the launch asks for what this scene's table needs
+  const size_t smem = TOP ? (size_t)p.scene.topCount * 32u : 0u;
   static int perSM = 0;
-  if (perSM == 0) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM,
-                                                                  traverseKernel<GEO, WIDE, COUNT>, 128, 0);
+  static size_t smemFor = ~(size_t)0;
+  if (perSM == 0 || smemFor != smem) {
+    cudaError_t e = cudaSuccess;
+    if (TOP)
+      e = cudaFuncSetAttribute(traverseKernel<GEO, WIDE, COUNT, TOP>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(VR_TOP_MAX * 32u));
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &perSM, traverseKernel<GEO, WIDE, COUNT, TOP>, T, smem);
     if (e != cudaSuccess)
       return e;
     if (perSM < 1)
       perSM = 1;
+    smemFor = smem;
   }
-  unsigned want = (p.numSlots + 127u) / 128u;
+  unsigned want = (p.numSlots + (unsigned)T - 1u) / (unsigned)T;
   unsigned grid = (unsigned)(numSMs * perSM);
   if (want < grid)
     grid = want;
-  traverseKernel<GEO, WIDE, COUNT><<<grid, 128, 0, s>>>(p);
+  traverseKernel<GEO, WIDE, COUNT, TOP><<<grid, T, smem, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -498,16 +607,28 @@ cudaError_t launchTraverse(const TraceParams &p, int numSMs, cudaStream_t s) {
     return cudaSuccess;
   const bool wide = p.scene.nodes4 != nullptr && p.scene.rootRef < VR_DONE;
   // the work counters (VR_COUNT_WORK) are compiled out of the normal kernels
+  // the shared-memory top of the tree only pays when there are rays enough to amortise
+  // one table copy per block
+  const bool top = !wide && p.scene.top != nullptr && p.scene.topCount > 0 &&
+                   p.scene.rootRef < VR_DONE && p.numSlots >= 65536u;
   const int which = (p.scene.geoType ? 4 : 0) | (wide ? 2 : 0) | (p.work ? 1 : 0);
+  if (top) {
+    switch (which) {
+    case 0: return launchTraverseT<0, 0, 0, 1>(p, numSMs, s);
+    case 1: return launchTraverseT<0, 0, 1, 1>(p, numSMs, s);
+    case 4: return launchTraverseT<1, 0, 0, 1>(p, numSMs, s);
+    default: return launchTraverseT<1, 0, 1, 1>(p, numSMs, s);
+    }
+  }
   switch (which) {
-  case 0: return launchTraverseT<0, 0, 0>(p, numSMs, s);
-  case 1: return launchTraverseT<0, 0, 1>(p, numSMs, s);
-  case 2: return launchTraverseT<0, 1, 0>(p, numSMs, s);
-  case 3: return launchTraverseT<0, 1, 1>(p, numSMs, s);
-  case 4: return launchTraverseT<1, 0, 0>(p, numSMs, s);
-  case 5: return launchTraverseT<1, 0, 1>(p, numSMs, s);
-  case 6: return launchTraverseT<1, 1, 0>(p, numSMs, s);
-  default: return launchTraverseT<1, 1, 1>(p, numSMs, s);
+  case 0: return launchTraverseT<0, 0, 0, 0>(p, numSMs, s);
+  case 1: return launchTraverseT<0, 0, 1, 0>(p, numSMs, s);
+  case 2: return launchTraverseT<0, 1, 0, 0>(p, numSMs, s);
+  case 3: return launchTraverseT<0, 1, 1, 0>(p, numSMs, s);
+  case 4: return launchTraverseT<1, 0, 0, 0>(p, numSMs, s);
+  case 5: return launchTraverseT<1, 0, 1, 0>(p, numSMs, s);
+  case 6: return launchTraverseT<1, 1, 0, 0>(p, numSMs, s);
+  default: return launchTraverseT<1, 1, 1, 0>(p, numSMs, s);
   }
 }
 
@@ -1109,6 +1230,7 @@ __global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ TraceP
         break;
     }
   }
+
   const unsigned lane = threadIdx.x & 31u;
   unsigned long long *cnt =
       p.counters + (size_t)((blockIdx.x * 4u + (threadIdx.x >> 5)) % VR_COUNTER_COPIES) * 8;
