@@ -47,6 +47,14 @@ typedef struct vr_ctx vr_ctx;
 
 /* replaces viennaray::Trace's RTCDevice (rayTrace.hpp:17,29) */
 int vr_ctx_create(int cudaDevice, vr_ctx **out);
+/* Several GPUs of one node behind one context: the scene calls are
+ * replicated on every device, vr_trace* shards the ray-index range over them (one host
+ * thread per device) and sums the result words with ONE ncclAllReduce over NVLink before
+ * the download; the flux is bit-identical to a single device tracing the whole range.
+ * NCCL is bound at run time (libnccl.so.2, or the path in VR_NCCL_LIB).  nDevices == 1 is
+ * vr_ctx_create(deviceIds[0]).  Every other entry point takes the returned context as is. */
+int vr_ctx_create_multi(int nDevices, const int *deviceIds, vr_ctx **out);
+int vr_ctx_num_devices(const vr_ctx *ctx);
 void vr_ctx_destroy(vr_ctx *ctx);
 /* message of the last failing call on ctx (ctx may be NULL for create) */
 const char *vr_last_error(const vr_ctx *ctx);
@@ -109,6 +117,13 @@ typedef struct {
   float coneMinAngle; /* coned cosine: cone = pi/2 - min(incAngle, this)     */
   float meanFreePath; /* getMeanFreePath(); <= 0: no scattering
                          (rayTraceKernel.hpp:179-203)                       */
+  /* Optional sticking probability per material: the kernel hands the materialId of the hit
+   * primitive to surfaceReflection (rayTraceKernel.hpp:310-313, rayParticle.hpp:44-48) and
+   * ViennaPS particles switch on it.  stickingByMaterial[m] replaces `sticking` when the hit
+   * primitive's materialId m (vr_scene_set_disks / vr_scene_set_triangles) lies in
+   * [0, numMaterials); host array, copied by vr_trace*.  NULL: constant sticking. */
+  const float *stickingByMaterial;
+  int32_t numMaterials;
 } vr_particle_desc;
 
 /* KernelConfig (rayUtil.hpp:83-94) + the ray-index shard of this context */
@@ -145,8 +160,9 @@ int vr_trace(vr_ctx *ctx, const vr_source_desc *source, const vr_particle_desc *
  * context's stream unless `sync` is non-zero. */
 int vr_trace_device(vr_ctx *ctx, const vr_source_desc *source, const vr_particle_desc *particles,
                     int numParticles, const vr_config *config, int sync);
-/* device pointer to numParticles x N uint64 fixed-point sums (internal
- * primitive order) followed by numParticles x 8 uint64 counters */
+/* device pointer to numParticles x N uint64 fixed-point sums in the CALLER's primitive order
+ * (so that ranks can sum them whatever BVH each one built) followed by numParticles x 8
+ * uint64 counters; vr_flux_download / vr_flux_postprocess read this buffer */
 int vr_flux_device(vr_ctx *ctx, void **devicePtr, size_t *numWords);
 int vr_flux_download(vr_ctx *ctx, double *fluxOut, vr_trace_info *infoOut);
 int vr_flux_download_fixed(vr_ctx *ctx, uint64_t *fluxOut);

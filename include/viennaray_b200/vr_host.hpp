@@ -372,6 +372,40 @@ public:
   }
 };
 
+/// A particle whose sticking probability depends on the material of the hit primitive --
+/// the pattern of ViennaPS's particles, which switch on the materialId that
+/// surfaceReflection receives (rayParticle.hpp:44-48, rayTraceKernel.hpp:310-313).
+/// `reflection`: VR_PARTICLE_DIFFUSE / _SPECULAR / _CONED_COSINE.  stickingByMaterial[m] is
+/// used for materialId m; IDs outside the table fall back to `stickingProbability`.
+/// Any user particle reaches the device the same way: by overriding deviceParticle().
+template <typename NumericType, int D>
+class MaterialStickingParticle
+    : public Particle<MaterialStickingParticle<NumericType, D>, NumericType> {
+  const int reflection_;
+  const NumericType sticking_, sourcePower_, minAngle_, meanFreePath_;
+  const std::vector<float> table_;
+  const std::string label_;
+
+public:
+  MaterialStickingParticle(int reflection, NumericType stickingProbability,
+                           std::vector<float> stickingByMaterial, NumericType sourcePower,
+                           std::string dataLabel, NumericType minAngle = 0,
+                           NumericType meanFreePath = -1)
+      : reflection_(reflection), sticking_(stickingProbability), sourcePower_(sourcePower),
+        minAngle_(minAngle), meanFreePath_(meanFreePath), table_(std::move(stickingByMaterial)),
+        label_(std::move(dataLabel)) {}
+  NumericType getSourceDistributionPower() const final { return sourcePower_; }
+  NumericType getMeanFreePath() const final { return meanFreePath_; }
+  [[nodiscard]] std::vector<std::string> getLocalDataLabels() const final { return {label_}; }
+  bool deviceParticle(vr_particle_desc &d) const final {
+    d = {reflection_, static_cast<float>(sticking_), static_cast<float>(sourcePower_),
+         static_cast<float>(minAngle_)};
+    d.stickingByMaterial = table_.empty() ? nullptr : table_.data();  // lives as long as *this
+    d.numMaterials = static_cast<std::int32_t>(table_.size());
+    return true;
+  }
+};
+
 // ---- sources (raySource.hpp:10-19) -------------------------------------------
 template <typename NumericType> class Source {
 public:
@@ -638,9 +672,38 @@ namespace viennaray {
 template <class NumericType, int D> class Trace {
 public:
   Trace() {
-    // device ordinal: VIENNARAY_B200_DEVICE (default 0; one process per GPU)
-    const char *dev = std::getenv("VIENNARAY_B200_DEVICE");
-    if (vr_ctx_create(dev ? std::atoi(dev) : 0, &ctx_) != VR_OK) {
+    // VIENNARAY_B200_DEVICES="0,1,2,3" (or "all"): several GPUs of the node behind this one
+    // object -- rays sharded over them, one NCCL all-reduce of the flux, no change for the
+    // caller.  Otherwise one device: VIENNARAY_B200_DEVICE (default 0).
+    std::vector<int> ids;
+    if (const char *list = std::getenv("VIENNARAY_B200_DEVICES")) {
+      const std::string l(list);
+      if (l == "all") {
+        for (int i = 0; i < 64; ++i) {  // probe: a plain context per ordinal until one fails
+          vr_ctx *probe = nullptr;
+          if (vr_ctx_create(i, &probe) != VR_OK)
+            break;
+          vr_ctx_destroy(probe);
+          ids.push_back(i);
+        }
+      } else {
+        std::size_t pos = 0;
+        while (pos < l.size()) {
+          const std::size_t end = l.find(',', pos);
+          const std::string tok = l.substr(pos, end == std::string::npos ? end : end - pos);
+          if (!tok.empty())
+            ids.push_back(std::atoi(tok.c_str()));
+          if (end == std::string::npos)
+            break;
+          pos = end + 1;
+        }
+      }
+    }
+    if (ids.empty()) {
+      const char *dev = std::getenv("VIENNARAY_B200_DEVICE");
+      ids.push_back(dev ? std::atoi(dev) : 0);
+    }
+    if (vr_ctx_create_multi(static_cast<int>(ids.size()), ids.data(), &ctx_) != VR_OK) {
       createError_ = vr_last_error(nullptr);
       ctx_ = nullptr;
     }
@@ -661,6 +724,7 @@ public:
   void setBoundaryConditions(BoundaryCondition boundaryConditions[D]) {
     for (int i = 0; i < D; ++i)
       boundaryConditions_[i] = boundaryConditions[i];
+    setupChanged();
   }
   void setSource(std::shared_ptr<Source<NumericType>> source) {
     pSource_ = std::move(source);
@@ -682,7 +746,10 @@ public:
   }
   void setMaxReflections(const unsigned maxReflections) { config_.maxReflections = maxReflections; }
   void setMaxBoundaryHits(const unsigned maxBoundaryHits) { config_.maxBoundaryHits = maxBoundaryHits; }
-  void setSourceDirection(const TraceDirection direction) { sourceDirection_ = direction; }
+  void setSourceDirection(const TraceDirection direction) {
+    sourceDirection_ = direction;
+    setupChanged();
+  }
   void setPrimaryDirection(const Vec3D<NumericType> primaryDirection) {
     primaryDirection_ = primaryDirection;
     usePrimaryDirection_ = true;
@@ -712,6 +779,10 @@ public:
   [[nodiscard]] vr_ctx *getDeviceContext() { return ctx_; }
 
 protected:
+  // boundary conditions / source direction changed: derived data that depends on them (the
+  // disk areas, which the reference recomputes in every apply(), rayTraceDisk.hpp:28)
+  virtual void setupChanged() {}
+
   // everything apply() needs besides the geometry: boundary, source, particle, config.
   // Returns false (with RTInfo_.error set) when the trace cannot run.
   bool traceCommitted(std::array<std::array<float, 3>, 2> bbox, float sourceOffset,
@@ -721,6 +792,8 @@ protected:
       VIENNACORE_LOG_ERROR("No B200 device context: " + createError_);
       return false;
     }
+    if (!pParticle_)  // reported by checkSettings(); nothing can be traced
+      return false;
     vr_particle_desc pd{};
     if (!pParticle_->deviceParticle(pd)) {
       RTInfo_.error = true;
@@ -860,10 +933,14 @@ public:
   ~TraceDisk() override = default;
 
   void apply() override {
-    if (!checkSettings())
-      return;
+    // like rayTraceDisk.hpp:19-20: every problem is reported and flagged, then the call goes
+    // on; what cannot run (no particle, no geometry, a source direction the geometry does not
+    // have) is refused by the stage that needs it, with RTInfo_.error set
+    checkSettings();
     const bool dirty = sceneDirty_;
-    if (dirty && !geometryOnDevice_) {
+    bool uploaded = !xyzr_.empty();
+    if (uploaded && dirty && !(geometryOnDevice_ && materialIds_.empty())) {
+      // (with material IDs the geometry goes up again: they arrive after setGeometry)
       const std::uint32_t n = static_cast<std::uint32_t>(numPoints());
       if (!this->ctx_ || vr_scene_set_disks(this->ctx_, xyzr_.data(), normals_.data(), n,
                                             materialIds_.empty() ? nullptr : materialIds_.data(),
@@ -871,12 +948,14 @@ public:
         this->RTInfo_.error = true;
         VIENNACORE_LOG_ERROR(std::string("Geometry upload failed: ") +
                              (this->ctx_ ? vr_last_error(this->ctx_) : this->createError_.c_str()));
-        return;
+        uploaded = false;
       }
     }
-    if (this->traceCommitted(bbox_, static_cast<float>(diskRadius_), numPoints(), dirty)) {
+    if (uploaded && this->traceCommitted(bbox_, static_cast<float>(diskRadius_), numPoints(), dirty)) {
       sceneDirty_ = false;
       this->haveSource_ = true;
+    } else {
+      ++this->config_.runNumber;  // rayTraceDisk.hpp:54 counts every apply()
     }
   }
 
@@ -946,8 +1025,12 @@ public:
     setGeometry(mesh.nodes, mesh.normals, static_cast<NumericType>(mesh.gridDelta));
   }
 
+  /// rayTraceDisk.hpp:96-98.  The IDs reach the device with the next apply(); a particle
+  /// whose deviceParticle() gives a sticking table (vr_particle_desc::stickingByMaterial) is
+  /// handed the ID of every disk it hits, as rayTraceKernel.hpp:290,310-313 does.
   template <typename T> void setMaterialIds(std::vector<T> const &materialIds) {
-    materialIds_.assign(materialIds.begin(), materialIds.end()); // not read by the built-in functors
+    materialIds_.assign(materialIds.begin(), materialIds.end());
+    sceneDirty_ = true;
   }
 
   // rayTraceDisk.hpp:103-142
@@ -1090,31 +1173,29 @@ private:
     }
   }
 
-  bool checkSettings() {
-    bool ok = true;
+  // rayTraceDisk.hpp:196-217: reports and flags, does not stop the call
+  void checkSettings() {
     if (this->pParticle_ == nullptr) {
       this->RTInfo_.error = true;
       VIENNACORE_LOG_ERROR("No particle was specified in rayTrace. Aborting.");
-      ok = false;
     }
     if (xyzr_.empty()) {
       this->RTInfo_.error = true;
       VIENNACORE_LOG_ERROR("No geometry was passed to rayTrace. Aborting.");
-      ok = false;
     }
     if (D == 2 && (this->sourceDirection_ == TraceDirection::POS_Z ||
                    this->sourceDirection_ == TraceDirection::NEG_Z)) {
       this->RTInfo_.error = true;
       VIENNACORE_LOG_ERROR("Invalid source direction in 2D geometry. Aborting.");
-      ok = false;
     }
     if (diskRadius_ > this->gridDelta_) {
       this->RTInfo_.warning = true;
       VIENNACORE_LOG_WARNING("Disk radius should be smaller than grid delta. Hit count "
                              "normalization not correct.");
     }
-    return ok;
   }
+
+  void setupChanged() override { diskAreas_.clear(); }
 
   std::vector<float> xyzr_, normals_;
   std::vector<std::uint32_t> nbOff_, nbIdx_;
@@ -1133,10 +1214,10 @@ public:
   ~TraceTriangle() override = default;
 
   void apply() override {
-    if (!checkSettings())
-      return;
+    checkSettings();  // rayTraceTriangle.hpp:19-20: reports and flags, the call goes on
     const bool dirty = sceneDirty_;
-    if (dirty) {
+    bool uploaded = !tris_.empty();
+    if (uploaded && dirty) {
       if (!this->ctx_ ||
           vr_scene_set_triangles(this->ctx_, verts_.data(), static_cast<std::uint32_t>(verts_.size() / 3),
                                  tris_.data(), static_cast<std::uint32_t>(tris_.size() / 3),
@@ -1145,12 +1226,15 @@ public:
         this->RTInfo_.error = true;
         VIENNACORE_LOG_ERROR(std::string("Geometry upload failed: ") +
                              (this->ctx_ ? vr_last_error(this->ctx_) : this->createError_.c_str()));
-        return;
+        uploaded = false;
       }
     }
-    if (this->traceCommitted(bbox_, static_cast<float>(this->gridDelta_), tris_.size() / 3, dirty)) {
+    if (uploaded &&
+        this->traceCommitted(bbox_, static_cast<float>(this->gridDelta_), tris_.size() / 3, dirty)) {
       sceneDirty_ = false;
       this->haveSource_ = true;
+    } else {
+      ++this->config_.runNumber;  // rayTraceTriangle.hpp:58 counts every apply()
     }
   }
 
@@ -1227,19 +1311,16 @@ public:
   void smoothFlux(std::vector<NumericType> &, int) override {} // no smoothing on elements
 
 private:
-  bool checkSettings() {
-    bool ok = true;
+  // rayTraceTriangle.hpp:129-138
+  void checkSettings() {
     if (this->pParticle_ == nullptr) {
       this->RTInfo_.error = true;
       VIENNACORE_LOG_ERROR("No particle was specified in rayTrace. Aborting.");
-      ok = false;
     }
     if (tris_.empty()) {
       this->RTInfo_.error = true;
       VIENNACORE_LOG_ERROR("No geometry was passed to rayTrace. Aborting.");
-      ok = false;
     }
-    return ok;
   }
 
   std::vector<float> verts_, normals_;

@@ -113,6 +113,14 @@ def oracle_lib():
     return _oracle
 
 
+def oracle_set_threads(n):
+    """OpenMP threads of the C oracle's traces (n <= 0: query); returns the count in effect."""
+    L = oracle_lib()
+    L.vro_set_threads.argtypes = [C.c_int]
+    L.vro_set_threads.restype = C.c_int
+    return int(L.vro_set_threads(int(n)))
+
+
 def have_ref():
     return os.path.exists(os.path.join(_REF, "libvr_ref.so"))
 

@@ -12,6 +12,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define INVALID_ID 0xffffffffu
 #define TNEAR 1e-4f /* rayUtil.hpp:218 fillRayPosition default tnear */
@@ -83,6 +86,11 @@ static inline uint32_t rng_u32(rng_t *r) {
   return r->buf[r->pos++];
 }
 /* uniform in [0,1): top 24 bits */
+/* The stream is consumed block-aligned per ray segment: the processing of every traced
+ * segment's hit starts at a fresh Philox block and the unused words of the previous one are
+ * dropped, so that the state a ray carries between the CUDA kernels is the block counter
+ * alone (vr_device.cuh, struct Rng). */
+static inline void rng_discard(rng_t *r) { r->pos = 4; }
 static inline float rng_f(rng_t *r) { return (float)(rng_u32(r) >> 8) * 5.9604644775390625e-8f; }
 
 /* ------------------------------------------------------------------------ */
@@ -237,6 +245,20 @@ struct vro_scene {
   uint32_t nNodes;
   uint32_t *primOrder;
 };
+
+/* threads of the following vro_trace calls (n <= 0: leave as is); returns the count in
+ * effect.  A launcher may export OMP_NUM_THREADS=1 to its workers (torch.distributed.run
+ * does): bench.py asks for the cores it reports. */
+int vro_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0)
+    omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
 
 /* Geometry::setMaterialIds, rayGeometry.hpp:19-26 (call after the primitives are set) */
 int vro_scene_set_material_ids(vro_scene *s, const int *ids) {
@@ -1075,6 +1097,7 @@ static void trace_one(const vro_scene *s, const vro_particle *p, const vro_confi
   for (;;) {
     hit_t h;
     intersect(s, org, dir, &h);
+    rng_discard(&rng); /* the draws of this segment start at a fresh block */
     info->totalTraces++;
     if (h.geom == INVALID_ID) { /* :172 */
       info->nonGeoHits++;

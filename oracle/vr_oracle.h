@@ -64,6 +64,7 @@ typedef struct {
       raysTerminated;
 } vro_info;
 
+int vro_set_threads(int n); /* n <= 0: query only; returns the OpenMP thread count in effect */
 vro_scene *vro_scene_create(int D);
 void vro_scene_destroy(vro_scene *s);
 int vro_scene_set_disks(vro_scene *s, const float *points, const float *normals, uint32_t n,

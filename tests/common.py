@@ -113,13 +113,14 @@ def product_setup(c):
     return out
 
 
-def make_gpu(c, device=0, primary_dir=None):
+def make_gpu(c, device=0, primary_dir=None, material_ids=None):
     st = product_setup(c)
     ctx = capi.Context(device)
     if c["geo"] == "disk":
-        ctx.set_disks(st["xyzr"], st["normals"], st["nb"][0], st["nb"][1])
+        ctx.set_disks(st["xyzr"], st["normals"], st["nb"][0], st["nb"][1],
+                      material_ids=material_ids)
     else:
-        ctx.set_triangles(st["verts"], st["tris"], st["normals"])
+        ctx.set_triangles(st["verts"], st["tris"], st["normals"], material_ids=material_ids)
     lo, hi = st["bbox"]
     _, first, second, _, _ = host.trace_settings(c["source_dir"])
     cond2 = c["bc"][second] if c["D"] == 3 else capi.BOUNDARY_IGNORE

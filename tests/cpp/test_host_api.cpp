@@ -6,7 +6,13 @@
 //   test_host_api gpu <outdir>   blocks that trace; flux arrays are dumped to
 //                                <outdir>/*.f32 for the Python side to compare
 //                                with the C-ABI / oracle path
+#include <rayGeometryDisk.hpp>
+#include <rayGeometryTriangle.hpp>
 #include <rayParticle.hpp>
+#include <rayPointNeighborhood.hpp>
+#include <rayReflection.hpp>
+#include <raySourceGrid.hpp>
+#include <raySourceRandom.hpp>
 #include <rayTraceDisk.hpp>
 #include <rayTraceTriangle.hpp>
 #include <rayTracingData.hpp>
@@ -202,6 +208,79 @@ static void testNoFallback() {
   noParticle.setGeometry(points, normals, 0.5f);
   noParticle.apply();
   VC_TEST_ASSERT(noParticle.getRayTraceInfo().error);
+}
+
+// the helper headers a consumer includes by their reference names (rayReflection.hpp,
+// raySourceRandom.hpp, rayPointNeighborhood.hpp, rayGeometry*.hpp): tests/reflection,
+// tests/pointNeighborhood, tests/createRay of the reference, on the host helpers
+static void testHostHelpers() {
+  RNG rng(42);
+  const Vec3D<float> down{0.f, 0.f, -1.f}, up{0.f, 0.f, 1.f};
+  const Vec3D<float> in45{0.70710678f, 0.f, -0.70710678f};
+  auto s = ReflectionSpecular<float, 3>(in45, up);
+  VC_TEST_ASSERT_ISCLOSE(s[0], 0.70710678f, 1e-6);
+  VC_TEST_ASSERT_ISCLOSE(s[2], 0.70710678f, 1e-6);
+  double meanCos = 0;
+  for (int i = 0; i < 20000; ++i) {
+    auto d = ReflectionDiffuse<float, 3>(up, rng);
+    VC_TEST_ASSERT(d[2] >= 0.f);
+    VC_TEST_ASSERT_ISCLOSE(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1.f, 1e-5);
+    meanCos += d[2];
+  }
+  VC_TEST_ASSERT_ISCLOSE(meanCos / 20000, 2. / 3., 0.01);  // cosine law: E[cos] = 2/3
+  VC_TEST_ASSERT((ReflectionDiffuse<float, 2>(Vec3D<float>{0.f, 1.f, 0.f}, rng)[2] == 0.f));
+  const float cone = 0.3f;
+  for (int i = 0; i < 2000; ++i) {  // stays inside the cone about the specular direction
+    auto d = ReflectionConedCosine<float, 3>(in45, up, rng, cone);
+    const float c = d[0] * s[0] + d[1] * s[1] + d[2] * s[2];
+    VC_TEST_ASSERT(c >= std::cos(cone) - 1e-4f && d[2] >= 0.f);
+  }
+  auto sp = ReflectionConedCosine<float, 3>(down, up, rng, 0.f);  // cone 0: specular
+  VC_TEST_ASSERT_ISCLOSE(sp[2], 1.f, 1e-6);
+
+  // tests/pointNeighborhood/pointNeighborhood.cpp: corner, edge, interior of a plane grid
+  std::vector<Vec3D<float>> points, normals;
+  planeGrid<float>(1.f, 3.f, {0, 1, 2}, points, normals);
+  PointNeighborhood<float, 3> nb;
+  nb.init<3>(points, 1.5f, Vec3D<float>{-3.f, -3.f, 0.f}, Vec3D<float>{3.f, 3.f, 0.f});
+  VC_TEST_ASSERT(nb.getNumPoints() == 49 && nb.getDistance() == 1.5f);
+  VC_TEST_ASSERT(nb.getNeighborIndices(0).size() == 3);
+  VC_TEST_ASSERT(nb.getNeighborIndices(1).size() == 5);
+  VC_TEST_ASSERT(nb.getNeighborIndices(8).size() == 8);
+
+  GeometryDisk<float, 3> geo;
+  geo.setMaterialIds(std::vector<int>(49, 7));
+  geo.initGeometry<3>(points, normals, 0.75f);
+  VC_TEST_ASSERT(geo.getNumPrimitives() == 49 && !geo.checkGeometryEmpty());
+  VC_TEST_ASSERT(geo.getMaterialId(5) == 7 && geo.getNeighborIndices(8).size() == 8);
+  VC_TEST_ASSERT(geo.getBoundingBox()[1][0] == 3.f && geo.getPrimNormal(3)[2] == 1.f);
+  GeometryTriangle<float, 3> tri;
+  tri.initGeometry({{0.f, 0.f, 0.f}, {2.f, 0.f, 0.f}, {0.f, 2.f, 0.f}}, {{0u, 1u, 2u}});
+  VC_TEST_ASSERT_ISCLOSE(tri.getPrimArea(0), 2.f, 1e-6);
+  VC_TEST_ASSERT_ISCLOSE(tri.getPrimNormal(0)[2], 1.f, 1e-6);
+
+  // tests/createRay/createRay.cpp: origins on the source plane, directions towards the geometry
+  std::array<Vec3D<float>, 2> bbox{Vec3D<float>{-1.f, -2.f, 0.f}, Vec3D<float>{1.f, 2.f, 5.f}};
+  auto st = rayInternal::getTraceSettings(TraceDirection::POS_Z);
+  std::array<Vec3D<float>, 3> basis{};
+  SourceRandom<float, 3> src(bbox, 3.f, st, 100, false, basis);
+  VC_TEST_ASSERT(src.getNumPoints() == 100 && src.getSourceArea() == 8.f);
+  for (int i = 0; i < 1000; ++i) {
+    auto od = src.getOriginAndDirection(i, rng);
+    VC_TEST_ASSERT(od[0][2] == 5.f && od[1][2] < 0.f);
+    VC_TEST_ASSERT(od[0][0] >= -1.f && od[0][0] <= 1.f && od[0][1] >= -2.f && od[0][1] <= 2.f);
+    VC_TEST_ASSERT_ISCLOSE(od[1][0] * od[1][0] + od[1][1] * od[1][1] + od[1][2] * od[1][2], 1.f, 1e-5);
+  }
+  vr_source_desc sd{};
+  std::vector<float> origins;
+  VC_TEST_ASSERT(src.deviceSource(sd, origins) && sd.rayDir == 2 && sd.useGrid == 0);
+
+  // a particle with material-dependent sticking maps to the descriptor's table
+  auto mp = std::make_unique<MaterialStickingParticle<float, 3>>(
+      VR_PARTICLE_DIFFUSE, 0.1f, std::vector<float>{0.05f, 0.6f}, 1.f, "flux");
+  vr_particle_desc pd{};
+  VC_TEST_ASSERT(mp->clone()->deviceParticle(pd) && pd.numMaterials == 2 &&
+                 pd.stickingByMaterial[1] == 0.6f && pd.sticking == 0.1f);
 }
 
 // ------------------------------------------------------------------ device blocks
@@ -422,6 +501,7 @@ int main(int argc, char **argv) {
   testNeighborsAndAreas();
   testBoundingBox();
   testNoFallback();
+  testHostHelpers();
   if (mode != "gpu")
     testSourceGrid("");
   if (mode == "gpu") {

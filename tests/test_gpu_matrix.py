@@ -31,13 +31,19 @@ def turned_trench(source_dir):
     return np.ascontiguousarray(pts), np.ascontiguousarray(nrm), gd
 
 
-def run_pair(c, num, max_refl=0xFFFFFFFF, max_bhits=1000, primary_dir=None, mfp=0.0, wdist=False):
+def run_pair(c, num, max_refl=0xFFFFFFFF, max_bhits=1000, primary_dir=None, mfp=0.0, wdist=False,
+             materials=None, table=None):
     orc = common.make_oracle(c)
-    ctx, src, _ = common.make_gpu(c, primary_dir=primary_dir)
+    ctx, src, _ = common.make_gpu(c, primary_dir=primary_dir, material_ids=materials)
     po_part = common.oracle_particle(c)
     po_part.meanFreePath = mfp
     g_part = common.gpu_particle(c)
     g_part.meanFreePath = mfp
+    if materials is not None:
+        orc.set_material_ids(materials)
+    if table is not None:
+        po_part.set_sticking_by_material(table)
+        g_part.set_sticking_by_material(table)
     fo, io = orc.trace(po_part,
                        orc.config(num, SEED, max_reflections=max_refl, max_boundary_hits=max_bhits,
                                   primary_dir=primary_dir, wdist=wdist))
@@ -141,6 +147,22 @@ def test_distance_weighted_spread(name, pname):
     run_pair(c, 60000, wdist=True)
     # and both options together
     run_pair(c, 30000, wdist=True, mfp=10.0)
+
+
+@pytest.mark.parametrize("name,table", [("trench", (0.05, 0.6)), ("trench_ion", (0.9, 0.1, 0.4)),
+                                        ("triangle3D", (0.02, 0.5)), ("disk2D", (0.3,)),
+                                        ("holes", (0.01, 1.0))])
+def test_sticking_by_material(name, table):
+    """The materialId of the hit primitive selects the sticking probability
+    (rayTraceKernel.hpp:310-313; the vr_particle_desc table).  IDs outside the table --
+    here the negative one and the one past its end -- keep the particle's constant."""
+    c = common.case(name)
+    n = len(c["points"]) if c["geo"] == "disk" else len(c["tris"])
+    mats = (np.arange(n) * 7919 % (len(table) + 2) - 1).astype(np.int32)  # -1 .. len(table)
+    d = run_pair(c, 60000, materials=mats, table=table)
+    d0 = run_pair(c, 60000, materials=mats)  # IDs without a table: the constant sticking
+    assert d["reflections"] != d0["reflections"]
+    run_pair(c, 30000, materials=mats, table=table, wdist=(c["geo"] == "disk"), mfp=15.0)
 
 
 @pytest.mark.parametrize("name", ["trench", "trench_ion", "triangle3D", "sphere2D"])

@@ -17,7 +17,8 @@ BOUNDARY_REFLECTIVE, BOUNDARY_PERIODIC, BOUNDARY_IGNORE = 0, 1, 2
 FLAG_WDIST = 1
 
 EXPORTS = [
-    "vr_ctx_create", "vr_ctx_destroy", "vr_last_error", "vr_scene_set_disks",
+    "vr_ctx_create", "vr_ctx_create_multi", "vr_ctx_num_devices", "vr_ctx_destroy",
+    "vr_last_error", "vr_scene_set_disks",
     "vr_scene_set_triangles", "vr_scene_build_neighbors", "vr_scene_get_neighbors",
     "vr_scene_set_boundary", "vr_source_set_grid", "vr_scene_commit", "vr_trace",
     "vr_trace_device", "vr_flux_device", "vr_flux_download", "vr_flux_download_fixed",
@@ -38,7 +39,19 @@ class SourceDesc(C.Structure):
 
 class ParticleDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("sticking", C.c_float), ("sourcePower", C.c_float),
-                ("coneMinAngle", C.c_float), ("meanFreePath", C.c_float)]
+                ("coneMinAngle", C.c_float), ("meanFreePath", C.c_float),
+                ("stickingByMaterial", C.c_void_p), ("numMaterials", C.c_int32)]
+
+    def set_sticking_by_material(self, table):
+        """sticking[materialId of the hit primitive]; None returns to the constant."""
+        if table is None:
+            self._table = None
+            self.stickingByMaterial, self.numMaterials = None, 0
+            return self
+        self._table = np.ascontiguousarray(table, np.float32)  # kept alive with the struct
+        self.stickingByMaterial = self._table.ctypes.data
+        self.numMaterials = len(self._table)
+        return self
 
 
 class Config(C.Structure):
@@ -77,6 +90,8 @@ def lib():
         L.vr_last_error.restype = C.c_char_p
         L.vr_last_error.argtypes = [_vp]
         L.vr_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
+        L.vr_ctx_create_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]
+        L.vr_ctx_num_devices.argtypes = [_vp]
         L.vr_ctx_destroy.restype = None
         L.vr_ctx_destroy.argtypes = [_vp]
         L.vr_scene_set_disks.argtypes = [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp]
@@ -141,17 +156,26 @@ def build_neighbors(D, points, distance):
 
 
 class Context:
-    """One vr_ctx: one GPU, one scene."""
+    """One vr_ctx: one scene on one GPU -- or, with a list of device ordinals, on several
+    GPUs of the node behind the same calls (vr_ctx_create_multi: rays sharded over the
+    devices, one NCCL all-reduce of the result words inside vr_trace*)."""
 
     def __init__(self, device=0):
         self.L = lib()
         h = _vp()
-        rc = self.L.vr_ctx_create(device, C.byref(h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self.L.vr_ctx_create_multi(len(device), ids, C.byref(h))
+        else:
+            rc = self.L.vr_ctx_create(int(device), C.byref(h))
         if rc:
             raise VrError(rc, self.L.vr_last_error(None).decode())
         self.h = h
         self.n = 0
         self.num_particles = 0
+
+    def num_devices(self):
+        return int(self.L.vr_ctx_num_devices(self.h))
 
     def close(self):
         if getattr(self, "h", None):

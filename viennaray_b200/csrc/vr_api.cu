@@ -8,13 +8,38 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <dlfcn.h>
 
 #include "vr_internal.h"
 
 using namespace vr;
 
+// NCCL, bound at run time (dlopen) so that the library carries no link-time dependency and a
+// process that already holds an NCCL -- torch's -- shares it.  Only the five entry points the
+// flux all-reduce needs; types as in nccl.h.
+typedef struct ncclComm *vrNcclComm;
+struct NcclApi {
+  void *lib = nullptr;
+  int (*commInitAll)(vrNcclComm *, int, const int *) = nullptr;
+  int (*commDestroy)(vrNcclComm) = nullptr;
+  int (*allReduce)(const void *, void *, size_t, int, int, vrNcclComm, cudaStream_t) = nullptr;
+  int (*groupStart)() = nullptr;
+  int (*groupEnd)() = nullptr;
+  const char *(*getErrorString)(int) = nullptr;
+};
+static const int VR_NCCL_UINT64 = 5, VR_NCCL_SUM = 0;  // ncclUint64, ncclSum (nccl.h)
+
 struct vr_ctx {
+  // A multi-device context (vr_ctx_create_multi) is a parent that owns one ordinary context
+  // per device: scene calls are replicated, a trace shards the ray-index range over the
+  // children (one host thread each), one NCCL all-reduce sums the result words, and the
+  // downloads read the first child.  `children` is empty for an ordinary context.
+  std::vector<vr_ctx *> children;
+  std::vector<vrNcclComm> comms;
+  NcclApi nccl;
   int device = 0;
   int numSMs = 0;
   cudaStream_t stream = nullptr;
@@ -37,13 +62,24 @@ struct vr_ctx {
   // device scene (internal = BVH order)
   float4 *dPrim = nullptr;
   uint32_t *dNbOff = nullptr, *dNbIdx = nullptr;
+  int *dMatId = nullptr;       // material IDs, internal order
+  float *dMatTab = nullptr;    // sticking tables of the running trace (all particles)
+  size_t matTabCap = 0;
+  std::vector<size_t> matTabOffset;
   Bvh bvh;
   DeviceScene scene{};
   bool committed = false;
 
-  // results of the last trace
-  unsigned long long *dResult = nullptr;  // np*n flux words + np*8 counters
+  // results of the last trace.  dResult: what the kernels add into, np*n flux words in
+  // internal (BVH) order + np*8 counters.  dFluxOrig: the same words in the CALLER's
+  // primitive order + the counters, written at the end of every trace; this is the buffer
+  // vr_flux_device exposes (a multi-GPU caller all-reduces it in place: its layout does
+  // not depend on the BVH a rank happened to build) and every download reads.
+  unsigned long long *dResult = nullptr;
   unsigned long long *dFluxOrig = nullptr;
+  size_t resultN = 0;       // primitives / particles the two buffers were sized for
+  int resultNp = 0;
+  bool resultValid = false; // dFluxOrig holds the flux of the committed scene's last trace
   unsigned long long *dCursor = nullptr;   // [0] ray cursor
   unsigned int *dSlotCursor = nullptr;      // [0] slot cursor, [1] live count
   unsigned long long *dCounterCopies = nullptr;  // VR_COUNTER_COPIES x 8
@@ -109,6 +145,8 @@ static void freeDeviceScene(vr_ctx *c) {
   cudaFreeAsync(c->dPrim, c->stream);
   cudaFreeAsync(c->dNbOff, c->stream);
   cudaFreeAsync(c->dNbIdx, c->stream);
+  cudaFreeAsync(c->dMatId, c->stream);
+  c->dMatId = nullptr;
   c->dPrim = nullptr;
   c->dNbOff = c->dNbIdx = nullptr;
   freeBvh(&c->bvh, c->stream);
@@ -142,6 +180,9 @@ static void freeResults(vr_ctx *c) {
   cudaFree(c->dFluxOrig);
   c->dResult = c->dFluxOrig = nullptr;
   c->resultWords = 0;
+  c->resultN = 0;
+  c->resultNp = 0;
+  c->resultValid = false;
   c->numParticles = 0;
 }
 
@@ -167,7 +208,7 @@ static cudaError_t allocOnePool(RayPool &q, uint32_t slots) {
   if ((e = cudaMalloc(&q.od0, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
       (e = cudaMalloc(&q.od1, sizeof(float2) * (size_t)slots)) != cudaSuccess ||
       (e = cudaMalloc(&q.hit, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
-      (e = cudaMalloc(&q.rng, sizeof(uint4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.rng, sizeof(uint32_t) * (size_t)slots)) != cudaSuccess ||
       (e = cudaMalloc(&q.meta, sizeof(uint4) * (size_t)slots)) != cudaSuccess ||
       (e = cudaMalloc(&q.weight, sizeof(float) * (size_t)slots)) != cudaSuccess ||
       (e = cudaMalloc(&q.dir3, sizeof(float4) * (size_t)slots)) != cudaSuccess)
@@ -186,6 +227,13 @@ static cudaError_t ensurePool(vr_ctx *c, uint32_t slots) {
   if (e != cudaSuccess)
     freePool(c);
   return e;
+}
+
+__global__ void gatherMaterialsKernel(const int *orig, const uint32_t *sortedToOrig, uint32_t n,
+                                      int *out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = orig[sortedToOrig[i]];
 }
 
 __global__ void reduceCountersKernel(const unsigned long long *copies, unsigned long long *out) {
@@ -223,6 +271,48 @@ static void collectMarks(vr_ctx *c) {
   c->tev.clear();
   c->tevKind.clear();
 }
+
+// ---- multi-device parent: helpers ---------------------------------------------------
+static bool loadNccl(NcclApi &a, std::string &why) {
+  const char *names[] = {getenv("VR_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) {
+    if (!nm || !*nm)
+      continue;
+    a.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+    if (a.lib)
+      break;
+  }
+  if (!a.lib) {
+    why = "NCCL not found (libnccl.so.2; set VR_NCCL_LIB to its path)";
+    return false;
+  }
+  a.commInitAll = (int (*)(vrNcclComm *, int, const int *))dlsym(a.lib, "ncclCommInitAll");
+  a.commDestroy = (int (*)(vrNcclComm))dlsym(a.lib, "ncclCommDestroy");
+  a.allReduce = (int (*)(const void *, void *, size_t, int, int, vrNcclComm, cudaStream_t))dlsym(
+      a.lib, "ncclAllReduce");
+  a.groupStart = (int (*)())dlsym(a.lib, "ncclGroupStart");
+  a.groupEnd = (int (*)())dlsym(a.lib, "ncclGroupEnd");
+  a.getErrorString = (const char *(*)(int))dlsym(a.lib, "ncclGetErrorString");
+  if (!a.commInitAll || !a.commDestroy || !a.allReduce || !a.groupStart || !a.groupEnd) {
+    why = "NCCL library lacks an expected symbol";
+    return false;
+  }
+  return true;
+}
+// first failing child's message becomes the parent's
+static int childFail(vr_ctx *parent, vr_ctx *child, int rc) {
+  parent->err = "device " + std::to_string(child->device) + ": " + child->err;
+  return rc;
+}
+#define EACH_CHILD(call)                                                                           \
+  do {                                                                                             \
+    for (vr_ctx * ch : ctx->children) {                                                            \
+      int rc_ = (call);                                                                            \
+      if (rc_ != VR_OK)                                                                            \
+        return childFail(ctx, ch, rc_);                                                            \
+    }                                                                                              \
+    return VR_OK;                                                                                  \
+  } while (0)
 
 extern "C" {
 
@@ -309,9 +399,63 @@ int vr_ctx_create(int cudaDevice, vr_ctx **out) {
   return VR_OK;
 }
 
+int vr_ctx_create_multi(int nDevices, const int *deviceIds, vr_ctx **out) {
+  if (!out)
+    return fail(nullptr, VR_ERR_ARGUMENT, "vr_ctx_create_multi: out is null");
+  *out = nullptr;
+  if (nDevices < 1 || !deviceIds)
+    return fail(nullptr, VR_ERR_ARGUMENT, "vr_ctx_create_multi: no devices given");
+  for (int i = 0; i < nDevices; ++i)
+    for (int j = 0; j < i; ++j)
+      if (deviceIds[i] == deviceIds[j])
+        return fail(nullptr, VR_ERR_ARGUMENT, "vr_ctx_create_multi: a device is listed twice");
+  if (nDevices == 1)
+    return vr_ctx_create(deviceIds[0], out);
+  vr_ctx *parent = new vr_ctx();
+  parent->device = deviceIds[0];
+  for (int i = 0; i < nDevices; ++i) {
+    vr_ctx *ch = nullptr;
+    int rc = vr_ctx_create(deviceIds[i], &ch);
+    if (rc != VR_OK) {
+      vr_ctx_destroy(parent);
+      return rc;  // g_createError holds the message
+    }
+    parent->children.push_back(ch);
+  }
+  std::string why;
+  if (!loadNccl(parent->nccl, why)) {
+    vr_ctx_destroy(parent);
+    return fail(nullptr, VR_ERR_UNSUPPORTED, "vr_ctx_create_multi: " + why);
+  }
+  parent->comms.assign((size_t)nDevices, nullptr);
+  int nrc = parent->nccl.commInitAll(parent->comms.data(), nDevices, deviceIds);
+  if (nrc != 0) {
+    std::string msg = parent->nccl.getErrorString ? parent->nccl.getErrorString(nrc) : "error";
+    parent->comms.clear();
+    vr_ctx_destroy(parent);
+    return fail(nullptr, VR_ERR_CUDA, "vr_ctx_create_multi: ncclCommInitAll: " + msg);
+  }
+  *out = parent;
+  return VR_OK;
+}
+
+int vr_ctx_num_devices(const vr_ctx *ctx) {
+  return !ctx ? 0 : (ctx->children.empty() ? 1 : (int)ctx->children.size());
+}
+
 void vr_ctx_destroy(vr_ctx *ctx) {
   if (!ctx)
     return;
+  if (!ctx->children.empty() || ctx->nccl.lib) {  // multi-device parent
+    for (size_t i = 0; i < ctx->comms.size(); ++i)
+      if (ctx->comms[i])
+        ctx->nccl.commDestroy(ctx->comms[i]);
+    for (vr_ctx *ch : ctx->children)
+      vr_ctx_destroy(ch);
+    // the NCCL handle stays open: unloading it under a process that shares it is not safe
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   if (ctx->stream) {
     freeDeviceScene(ctx);
@@ -328,6 +472,7 @@ void vr_ctx_destroy(vr_ctx *ctx) {
     if (e)
       cudaEventDestroy(e);
   freePool(ctx);
+  cudaFree(ctx->dMatTab);
   cudaFree(ctx->dWork);
   if (ctx->ev0)
     cudaEventDestroy(ctx->ev0);
@@ -338,18 +483,40 @@ void vr_ctx_destroy(vr_ctx *ctx) {
   delete ctx;
 }
 
-void *vr_ctx_stream(vr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+void *vr_ctx_stream(vr_ctx *ctx) {
+  if (ctx && !ctx->children.empty())
+    return vr_ctx_stream(ctx->children[0]);
+  return ctx ? (void *)ctx->stream : nullptr;
+}
 int vr_ctx_synchronize(vr_ctx *ctx) {
   if (!ctx)
     return VR_ERR_ARGUMENT;
+  if (!ctx->children.empty())
+    EACH_CHILD(vr_ctx_synchronize(ch));
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   return VR_OK;
 }
-float vr_last_kernel_ms(vr_ctx *ctx) { return ctx ? ctx->lastMs : 0.f; }
+float vr_last_kernel_ms(vr_ctx *ctx) {
+  if (ctx && !ctx->children.empty())
+    return ctx->lastMs;  // slowest device of the last trace
+  return ctx ? ctx->lastMs : 0.f;
+}
 int vr_last_launch_count(vr_ctx *ctx, int *kernelsOut, int *iterationsOut) {
   if (!ctx)
     return VR_ERR_ARGUMENT;
+  if (!ctx->children.empty()) {  // summed over the devices
+    int k = 0, it = 0;
+    for (vr_ctx *ch : ctx->children) {
+      k += ch->kernelLaunches;
+      it += ch->iterations;
+    }
+    if (kernelsOut)
+      *kernelsOut = k;
+    if (iterationsOut)
+      *iterationsOut = it;
+    return VR_OK;
+  }
   if (kernelsOut)
     *kernelsOut = ctx->kernelLaunches;
   if (iterationsOut)
@@ -360,6 +527,8 @@ int vr_last_launch_count(vr_ctx *ctx, int *kernelsOut, int *iterationsOut) {
 int vr_scene_set_disks(vr_ctx *ctx, const float *xyzr, const float *nxyz, uint32_t n,
                        const int32_t *materialIds, const uint32_t *nbOffsets,
                        const uint32_t *nbIndices) {
+  if (ctx && !ctx->children.empty())
+    EACH_CHILD(vr_scene_set_disks(ch, xyzr, nxyz, n, materialIds, nbOffsets, nbIndices));
   if (!ctx)
     return VR_ERR_ARGUMENT;
   if (!xyzr || !nxyz || n == 0)
@@ -382,6 +551,7 @@ int vr_scene_set_disks(vr_ctx *ctx, const float *xyzr, const float *nxyz, uint32
   }
   CK(cudaSetDevice(ctx->device));
   ctx->committed = false;
+  ctx->resultValid = false;  // results belong to the scene that was traced
   freeInputs(ctx);
   ctx->geoType = 0;
   ctx->n = n;
@@ -416,6 +586,8 @@ int vr_scene_set_disks(vr_ctx *ctx, const float *xyzr, const float *nxyz, uint32
 
 int vr_scene_set_triangles(vr_ctx *ctx, const float *verts, uint32_t nVerts, const uint32_t *idx,
                            uint32_t n, const float *normals, const int32_t *materialIds) {
+  if (ctx && !ctx->children.empty())
+    EACH_CHILD(vr_scene_set_triangles(ch, verts, nVerts, idx, n, normals, materialIds));
   if (!ctx)
     return VR_ERR_ARGUMENT;
   if (!verts || !idx || !normals || n == 0 || nVerts == 0)
@@ -427,6 +599,7 @@ int vr_scene_set_triangles(vr_ctx *ctx, const float *verts, uint32_t nVerts, con
       return fail(ctx, VR_ERR_ARGUMENT, "vr_scene_set_triangles: vertex index out of range");
   CK(cudaSetDevice(ctx->device));
   ctx->committed = false;
+  ctx->resultValid = false;  // results belong to the scene that was traced
   freeInputs(ctx);
   ctx->geoType = 1;
   ctx->n = n;
@@ -454,6 +627,8 @@ int vr_scene_set_triangles(vr_ctx *ctx, const float *verts, uint32_t nVerts, con
 }
 
 int vr_source_set_grid(vr_ctx *ctx, const float *points, uint32_t n) {
+  if (ctx && !ctx->children.empty())
+    EACH_CHILD(vr_source_set_grid(ch, points, n));
   if (!ctx)
     return VR_ERR_ARGUMENT;
   if (n && !points)
@@ -471,6 +646,8 @@ int vr_source_set_grid(vr_ctx *ctx, const float *points, uint32_t n) {
 }
 
 int vr_scene_build_neighbors(vr_ctx *ctx, int D, const float *points, float distance) {
+  if (ctx && !ctx->children.empty())
+    EACH_CHILD(vr_scene_build_neighbors(ch, D, points, distance));
   if (!ctx)
     return VR_ERR_ARGUMENT;
   if (!points || (D != 2 && D != 3) || !(distance > 0.f))
@@ -484,6 +661,7 @@ int vr_scene_build_neighbors(vr_ctx *ctx, int D, const float *points, float dist
     for (int a = 0; a < D; ++a)
       lo[a] = std::min(lo[a], points[3 * (size_t)i + a]);
   ctx->committed = false;
+  ctx->resultValid = false;  // results belong to the scene that was traced
   cudaFreeAsync(ctx->dNbOffO, ctx->stream);
   cudaFreeAsync(ctx->dNbIdxO, ctx->stream);
   ctx->dNbOffO = ctx->dNbIdxO = nullptr;
@@ -503,6 +681,8 @@ int vr_scene_build_neighbors(vr_ctx *ctx, int D, const float *points, float dist
 }
 
 int vr_scene_get_neighbors(vr_ctx *ctx, uint32_t **offsetsOut, uint32_t **indicesOut) {
+  if (ctx && !ctx->children.empty())
+    return vr_scene_get_neighbors(ctx->children[0], offsetsOut, indicesOut);
   if (!ctx || !offsetsOut || !indicesOut)
     return VR_ERR_ARGUMENT;
   if (ctx->geoType != 0 || !ctx->dNbOffO)
@@ -530,6 +710,8 @@ int vr_scene_get_neighbors(vr_ctx *ctx, uint32_t **offsetsOut, uint32_t **indice
 
 int vr_scene_set_boundary(vr_ctx *ctx, const float bboxMin[3], const float bboxMax[3],
                           int firstDir, int secondDir, int condFirst, int condSecond, int D) {
+  if (ctx && !ctx->children.empty())
+    EACH_CHILD(vr_scene_set_boundary(ch, bboxMin, bboxMax, firstDir, secondDir, condFirst, condSecond, D));
   if (!ctx)
     return VR_ERR_ARGUMENT;
   if (!bboxMin || !bboxMax || (D != 2 && D != 3) || firstDir < 0 || firstDir > 2 ||
@@ -565,6 +747,18 @@ int vr_scene_set_boundary(vr_ctx *ctx, const float bboxMin[3], const float bboxM
         s.btri[i][k][a] = v[planes[firstDir][i][k]][a];
         s.btri[i + 4][k][a] = v[planes[secondDir][i][k]][a];
       }
+  for (int e = 0; e < 2; ++e) {
+    const int a = e ? secondDir : firstDir, b = (a + 1) % 3, c = (a + 2) % 3;
+    s.bnd[e].a = a;
+    s.bnd[e].b = b;
+    s.bnd[e].c = c;
+    // the float differences / product testTri forms from the vertices above
+    const volatile float Lb = s.bbox[1][b] - s.bbox[0][b], Lc = s.bbox[1][c] - s.bbox[0][c];
+    const volatile float P = Lc * Lb;
+    s.bnd[e].Lb = Lb;
+    s.bnd[e].Lc = Lc;
+    s.bnd[e].P = P;
+  }
   ctx->boundarySet = true;
   return VR_OK;
 }
@@ -573,6 +767,8 @@ int vr_scene_set_boundary(vr_ctx *ctx, const float bboxMin[3], const float bboxM
 // padded boxes, Morton sort + LBVH, the permutation of the primitives into BVH
 // order and the remapping of the neighbour lists into that index space.
 int vr_scene_commit(vr_ctx *ctx) {
+  if (ctx && !ctx->children.empty())
+    EACH_CHILD(vr_scene_commit(ch));
   if (!ctx)
     return VR_ERR_ARGUMENT;
   if (ctx->geoType < 0)
@@ -646,6 +842,18 @@ int vr_scene_commit(vr_ctx *ctx) {
   CKT(cudaMallocAsync(&cnt, sizeof(uint32_t) * n, st));
   CKT(remapNeighbors(ctx->bvh.sortedToOrig, ctx->dNbOffO, ctx->dNbIdxO, n, o2s, cnt, ctx->dNbOff,
                      ctx->dNbIdx, st));
+  {  // material IDs into the internal (BVH) order
+    int *matOrig = nullptr;
+    CKT(uploadArray(ctx, &matOrig, ctx->materialIds.data(), (size_t)n));
+    cudaError_t em = cudaMallocAsync(&ctx->dMatId, sizeof(int) * (size_t)n, st);
+    if (em == cudaSuccess) {
+      gatherMaterialsKernel<<<(n + 255) / 256, 256, 0, st>>>(matOrig, ctx->bvh.sortedToOrig, n,
+                                                             ctx->dMatId);
+      em = cudaGetLastError();
+    }
+    cudaFreeAsync(matOrig, st);
+    CKT(em);
+  }
   tmpFree();
 #undef CKT
   CK(cudaStreamSynchronize(st));
@@ -686,6 +894,15 @@ static int fillParams(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_
   p.scene = ctx->scene;
   p.src = *src;
   p.particle = *part;
+  p.particle.stickingByMaterial = nullptr;  // host pointer: the device copy is p.matSticking
+  p.matId = ctx->dMatId;
+  p.matSticking = nullptr;
+  p.numMaterials = 0;
+  if (part->stickingByMaterial && part->numMaterials > 0 && ctx->dMatTab &&
+      (size_t)particleIndex < ctx->matTabOffset.size()) {
+    p.matSticking = ctx->dMatTab + ctx->matTabOffset[particleIndex];
+    p.numMaterials = part->numMaterials;
+  }
   p.ee = 1.0f / (part->sourcePower + 1.0f);
   p.eeGrid = 2.0f / (part->sourcePower + 1.0f);
   p.grid = nullptr;
@@ -717,10 +934,72 @@ static int fillParams(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_
   return VR_OK;
 }
 
+// Multi-device trace: device g of G traces the g-th contiguous slice of [rayIdxBegin,
+// rayIdxEnd) (a ray's walk depends only on (seed, particle, index), so the union of the slices
+// is the single-device job); one host thread per device drives its wavefront, then ONE
+// ncclAllReduce(sum) over the uint64 result words (flux in the caller's primitive order +
+// counters), queued on every device's stream.  Integer sums: the result is bit-identical to
+// one device tracing the whole range.
+static int traceMulti(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_desc *particles,
+                      int np, const vr_config *cfg, int sync) {
+  if (!cfg)
+    return fail(ctx, VR_ERR_ARGUMENT, "trace: null descriptor");
+  if (cfg->rayIdxEnd < cfg->rayIdxBegin || cfg->rayIdxEnd > cfg->numRays)
+    return fail(ctx, VR_ERR_ARGUMENT, "trace: ray index shard out of range");
+  const size_t G = ctx->children.size();
+  const uint64_t total = cfg->rayIdxEnd - cfg->rayIdxBegin;
+  std::vector<int> rcs(G, VR_OK);
+  std::vector<std::thread> threads;
+  for (size_t g = 0; g < G; ++g) {
+    vr_config c = *cfg;
+    const uint64_t base = total / G, rem = total % G;
+    c.rayIdxBegin = cfg->rayIdxBegin + g * base + std::min<uint64_t>(g, rem);
+    c.rayIdxEnd = c.rayIdxBegin + base + (g < rem ? 1 : 0);
+    threads.emplace_back([=, &rcs]() {
+      rcs[g] = vr_trace_device(ctx->children[g], src, particles, np, &c, 0);
+    });
+  }
+  for (auto &t : threads)
+    t.join();
+  for (size_t g = 0; g < G; ++g)
+    if (rcs[g] != VR_OK)
+      return childFail(ctx, ctx->children[g], rcs[g]);
+  const size_t words = ctx->children[0]->resultWords;
+  int nrc = ctx->nccl.groupStart();
+  for (size_t g = 0; g < G && nrc == 0; ++g) {
+    vr_ctx *ch = ctx->children[g];
+    nrc = ctx->nccl.allReduce(ch->dFluxOrig, ch->dFluxOrig, words, VR_NCCL_UINT64, VR_NCCL_SUM,
+                              ctx->comms[g], ch->stream);
+  }
+  const int erc = ctx->nccl.groupEnd();
+  if (nrc == 0)
+    nrc = erc;
+  if (nrc != 0)
+    return fail(ctx, VR_ERR_CUDA, std::string("trace: ncclAllReduce: ") +
+                                      (ctx->nccl.getErrorString ? ctx->nccl.getErrorString(nrc) : "error"));
+  ctx->lastMs = 0.f;
+  for (vr_ctx *ch : ctx->children) {
+    ch->lastNumRays = total;  // TraceInfo.numRays of the whole job
+    if (sync) {
+      CK(cudaSetDevice(ch->device));
+      CK(cudaStreamSynchronize(ch->stream));
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ch->ev0, ch->ev1) == cudaSuccess)
+        ctx->lastMs = std::max(ctx->lastMs, ms);
+    }
+  }
+  if (sync)
+    for (vr_ctx *ch : ctx->children)
+      ch->lastMs = ctx->lastMs;
+  return VR_OK;
+}
+
 int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_desc *particles,
                     int np, const vr_config *cfg, int sync) {
   if (!ctx)
     return VR_ERR_ARGUMENT;
+  if (!ctx->children.empty())
+    return traceMulti(ctx, src, particles, np, cfg, sync);
   if (!ctx->committed)
     return fail(ctx, VR_ERR_STATE, "trace: scene not committed");
   if (np < 1 || !particles)
@@ -728,14 +1007,40 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
   CK(cudaSetDevice(ctx->device));
   const size_t n = ctx->n;
   const size_t words = (size_t)np * n + (size_t)np * 8;
-  if (words != ctx->resultWords) {
-    freeResults(ctx);
+  if (n != ctx->resultN || np != ctx->resultNp) {  // (np, n), not their product: (2, 46) and
+    freeResults(ctx);                              // (1, 100) have the same word count
     CK(cudaMalloc(&ctx->dResult, sizeof(unsigned long long) * words));
-    CK(cudaMalloc(&ctx->dFluxOrig, sizeof(unsigned long long) * (size_t)np * n));
+    CK(cudaMalloc(&ctx->dFluxOrig, sizeof(unsigned long long) * words));
     ctx->resultWords = words;
+    ctx->resultN = n;
+    ctx->resultNp = np;
   }
+  ctx->resultValid = false;
   ctx->numParticles = np;
   ctx->lastNumRays = cfg ? cfg->rayIdxEnd - cfg->rayIdxBegin : 0;
+  {  // sticking tables by material, one after the other
+    std::vector<float> tab;
+    ctx->matTabOffset.assign((size_t)np, 0);
+    for (int k = 0; k < np; ++k) {
+      ctx->matTabOffset[k] = tab.size();
+      if (particles[k].stickingByMaterial && particles[k].numMaterials > 0)
+        tab.insert(tab.end(), particles[k].stickingByMaterial,
+                   particles[k].stickingByMaterial + particles[k].numMaterials);
+    }
+    if (!tab.empty()) {
+      if (tab.size() > ctx->matTabCap) {
+        cudaFree(ctx->dMatTab);
+        ctx->dMatTab = nullptr;
+        ctx->matTabCap = 0;
+        CK(cudaMalloc(&ctx->dMatTab, sizeof(float) * tab.size()));
+        ctx->matTabCap = tab.size();
+      }
+      // pageable source: the copy has read `tab` when the call returns
+      CK(cudaMemcpyAsync(ctx->dMatTab, tab.data(), sizeof(float) * tab.size(),
+                         cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+  }
   CK(cudaMemsetAsync(ctx->dResult, 0, sizeof(unsigned long long) * words, ctx->stream));
   if (ctx->countWork)
     CK(cudaMemsetAsync(ctx->dWork, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -887,7 +1192,22 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
         p.numSlots = bound;
         mark(ctx, 2);
         p.spreadQ = nullptr;  // the tail kernel spreads inline
+        cudaEvent_t tl[2] = {nullptr, nullptr};
+        if (ctx->dumpLaunches) {
+          cudaEventCreate(&tl[0]);
+          cudaEventCreate(&tl[1]);
+          cudaEventRecord(tl[0], ctx->stream);
+        }
         CK(launchTail(p, ctx->stream));
+        if (tl[0]) {
+          float ms = 0.f;
+          cudaEventRecord(tl[1], ctx->stream);
+          cudaEventSynchronize(tl[1]);
+          cudaEventElapsedTime(&ms, tl[0], tl[1]);
+          fprintf(stderr, "[vr] particle %d tail kernel: %u rays, %.4f ms\n", k, live, ms);
+          cudaEventDestroy(tl[0]);
+          cudaEventDestroy(tl[1]);
+        }
         mark(ctx, 1);
         ctx->kernelLaunches += 1;
         ++ctx->iterations;
@@ -898,6 +1218,14 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
                                                     ctx->dResult + (size_t)np * n + (size_t)k * 8);
     CK(cudaGetLastError());
   }
+  // the result in the caller's primitive order (+ the counters behind it)
+  for (int k = 0; k < np; ++k)
+    CK(launchUnsortFlux(ctx->dResult + (size_t)k * n, ctx->bvh.sortedToOrig, (uint32_t)n,
+                        ctx->dFluxOrig + (size_t)k * n, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dFluxOrig + (size_t)np * n, ctx->dResult + (size_t)np * n,
+                     sizeof(unsigned long long) * (size_t)np * 8, cudaMemcpyDeviceToDevice,
+                     ctx->stream));
+  ctx->resultValid = true;
   mark(ctx, 2);
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (sync) {
@@ -914,31 +1242,29 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
 }
 
 int vr_flux_device(vr_ctx *ctx, void **devicePtr, size_t *numWords) {
+  if (ctx && !ctx->children.empty())
+    return vr_flux_device(ctx->children[0], devicePtr, numWords);
   if (!ctx || !devicePtr || !numWords)
     return VR_ERR_ARGUMENT;
-  if (!ctx->dResult)
-    return fail(ctx, VR_ERR_STATE, "vr_flux_device: no trace has run");
-  *devicePtr = ctx->dResult;
+  if (!ctx->dFluxOrig || !ctx->resultValid)
+    return fail(ctx, VR_ERR_STATE, "vr_flux_device: no trace has run on the current scene");
+  *devicePtr = ctx->dFluxOrig;
   *numWords = ctx->resultWords;
   return VR_OK;
 }
 
 static int downloadFixed(vr_ctx *ctx, std::vector<unsigned long long> &flux,
                          std::vector<unsigned long long> &counters) {
-  if (!ctx->dResult)
-    return fail(ctx, VR_ERR_STATE, "download: no trace has run");
+  if (!ctx->dFluxOrig || !ctx->resultValid)
+    return fail(ctx, VR_ERR_STATE, "download: no trace has run on the current scene");
   CK(cudaSetDevice(ctx->device));
-
-  const size_t n = ctx->n, np = ctx->numParticles;
-  for (size_t k = 0; k < np; ++k)
-    CK(launchUnsortFlux(ctx->dResult + k * n, ctx->bvh.sortedToOrig, (uint32_t)n,
-                        ctx->dFluxOrig + k * n, ctx->stream));
+  const size_t n = ctx->resultN, np = ctx->resultNp;
   flux.resize(np * n);
   counters.resize(np * 8);
   CK(cudaMemcpyAsync(flux.data(), ctx->dFluxOrig, sizeof(unsigned long long) * np * n,
                      cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(counters.data(), ctx->dResult + np * n, sizeof(unsigned long long) * np * 8,
-                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(counters.data(), ctx->dFluxOrig + np * n,
+                     sizeof(unsigned long long) * np * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (cudaEventQuery(ctx->ev1) == cudaSuccess)
     cudaEventElapsedTime(&ctx->lastMs, ctx->ev0, ctx->ev1);
@@ -946,6 +1272,11 @@ static int downloadFixed(vr_ctx *ctx, std::vector<unsigned long long> &flux,
 }
 
 int vr_flux_download(vr_ctx *ctx, double *fluxOut, vr_trace_info *infoOut) {
+  if (ctx && !ctx->children.empty())
+    {
+      int rc_ = vr_flux_download(ctx->children[0], fluxOut, infoOut);
+      return rc_ ? childFail(ctx, ctx->children[0], rc_) : VR_OK;
+    };
   if (!ctx)
     return VR_ERR_ARGUMENT;
   std::vector<unsigned long long> flux, counters;
@@ -974,10 +1305,15 @@ int vr_flux_download(vr_ctx *ctx, double *fluxOut, vr_trace_info *infoOut) {
 
 int vr_flux_postprocess(vr_ctx *ctx, int particle, const float *areas, float normFactor,
                         int smooth, float *fluxOut) {
+  if (ctx && !ctx->children.empty())
+    {
+      int rc_ = vr_flux_postprocess(ctx->children[0], particle, areas, normFactor, smooth, fluxOut);
+      return rc_ ? childFail(ctx, ctx->children[0], rc_) : VR_OK;
+    };
   if (!ctx || !fluxOut)
     return VR_ERR_ARGUMENT;
-  if (!ctx->dResult || !ctx->committed)
-    return fail(ctx, VR_ERR_STATE, "vr_flux_postprocess: no trace has run");
+  if (!ctx->dFluxOrig || !ctx->resultValid || !ctx->committed)
+    return fail(ctx, VR_ERR_STATE, "vr_flux_postprocess: no trace has run on the current scene");
   if (particle < 0 || particle >= ctx->numParticles)
     return fail(ctx, VR_ERR_ARGUMENT, "vr_flux_postprocess: particle index out of range");
   CK(cudaSetDevice(ctx->device));
@@ -988,7 +1324,7 @@ int vr_flux_postprocess(vr_ctx *ctx, int particle, const float *areas, float nor
   if (areas)
     e = cudaMemcpyAsync(buf, areas, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess)
-    e = postprocessFlux(ctx->scene, ctx->dResult + (size_t)particle * n, ctx->bvh.sortedToOrig,
+    e = postprocessFlux(ctx->scene, ctx->dFluxOrig + (size_t)particle * n, ctx->bvh.sortedToOrig,
                         areas ? buf : nullptr, normFactor, smooth, buf + n, buf + 2 * n,
                         buf + 3 * n, ctx->stream);
   if (e == cudaSuccess)
@@ -1003,6 +1339,11 @@ int vr_flux_postprocess(vr_ctx *ctx, int particle, const float *areas, float nor
 }
 
 int vr_flux_download_fixed(vr_ctx *ctx, uint64_t *fluxOut) {
+  if (ctx && !ctx->children.empty())
+    {
+      int rc_ = vr_flux_download_fixed(ctx->children[0], fluxOut);
+      return rc_ ? childFail(ctx, ctx->children[0], rc_) : VR_OK;
+    };
   if (!ctx || !fluxOut)
     return VR_ERR_ARGUMENT;
   std::vector<unsigned long long> flux, counters;
@@ -1093,6 +1434,8 @@ void vr_free(void *p) { free(p); }
 int vr_debug_intersect(vr_ctx *ctx, const float *rays, uint32_t m, uint32_t *geomOut,
                        uint32_t *primOut, float *tOut, uint32_t nbCap, uint32_t *nbCountOut,
                        uint32_t *nbOut) {
+  if (ctx && !ctx->children.empty())
+    return vr_debug_intersect(ctx->children[0], rays, m, geomOut, primOut, tOut, nbCap, nbCountOut, nbOut);
   if (!ctx || !rays || !geomOut || !primOut || !tOut)
     return VR_ERR_ARGUMENT;
   if (!ctx->committed)
@@ -1168,6 +1511,8 @@ int vr_debug_intersect(vr_ctx *ctx, const float *rays, uint32_t m, uint32_t *geo
 
 int vr_debug_source_rays(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_desc *part,
                          const vr_config *cfg, uint64_t idxBegin, uint32_t m, float *raysOut) {
+  if (ctx && !ctx->children.empty())
+    return vr_debug_source_rays(ctx->children[0], src, part, cfg, idxBegin, m, raysOut);
   if (!ctx || !raysOut)
     return VR_ERR_ARGUMENT;
   if (!ctx->boundarySet)
@@ -1192,6 +1537,8 @@ int vr_debug_source_rays(vr_ctx *ctx, const vr_source_desc *src, const vr_partic
 }
 
 int vr_debug_math(vr_ctx *ctx, int which, const float *x, uint32_t m, float param, float *out) {
+  if (ctx && !ctx->children.empty())
+    return vr_debug_math(ctx->children[0], which, x, m, param, out);
   if (!ctx || !x || !out || which < 0 || which > 2)
     return VR_ERR_ARGUMENT;
   CK(cudaSetDevice(ctx->device));
@@ -1216,6 +1563,8 @@ int vr_debug_math(vr_ctx *ctx, int which, const float *x, uint32_t m, float para
 
 int vr_debug_philox(vr_ctx *ctx, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
                     uint32_t c3, uint32_t *out4) {
+  if (ctx && !ctx->children.empty())
+    return vr_debug_philox(ctx->children[0], k0, k1, c0, c1, c2, c3, out4);
   if (!ctx || !out4)
     return VR_ERR_ARGUMENT;
   CK(cudaSetDevice(ctx->device));
@@ -1234,6 +1583,8 @@ int vr_debug_philox(vr_ctx *ctx, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t
 
 int vr_debug_reflect(vr_ctx *ctx, int kind, int D, const float *rayDir, const float *normal,
                      float coneMinAngle, uint32_t seed, uint64_t idx, uint32_t m, float *out3) {
+  if (ctx && !ctx->children.empty())
+    return vr_debug_reflect(ctx->children[0], kind, D, rayDir, normal, coneMinAngle, seed, idx, m, out3);
   if (!ctx || !rayDir || !normal || !out3 || (D != 2 && D != 3) || kind < 0 || kind > 2)
     return VR_ERR_ARGUMENT;
   CK(cudaSetDevice(ctx->device));
@@ -1253,6 +1604,8 @@ int vr_debug_reflect(vr_ctx *ctx, int kind, int D, const float *rayDir, const fl
 }
 
 int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out5) {
+  if (ctx && !ctx->children.empty())
+    return vr_debug_bvh_stats(ctx->children[0], out5);
   if (!ctx || !out5)
     return VR_ERR_ARGUMENT;
   if (!ctx->committed)
@@ -1274,6 +1627,8 @@ int vr_debug_bvh_stats(vr_ctx *ctx, uint64_t *out5) {
 }
 
 int vr_debug_phase_timing(vr_ctx *ctx, int enable) {
+  if (ctx && !ctx->children.empty())
+    EACH_CHILD(vr_debug_phase_timing(ch, enable));
   if (!ctx)
     return VR_ERR_ARGUMENT;
   ctx->timeKernels = enable != 0;
@@ -1285,6 +1640,8 @@ int vr_debug_phase_timing(vr_ctx *ctx, int enable) {
 }
 
 int vr_debug_phase_ms(vr_ctx *ctx, double *ms3, int64_t *launches3) {
+  if (ctx && !ctx->children.empty())
+    return vr_debug_phase_ms(ctx->children[0], ms3, launches3);
   if (!ctx || !ms3)
     return VR_ERR_ARGUMENT;
   CK(cudaSetDevice(ctx->device));
@@ -1299,6 +1656,8 @@ int vr_debug_phase_ms(vr_ctx *ctx, double *ms3, int64_t *launches3) {
 }
 
 int vr_debug_work_counters(vr_ctx *ctx, uint64_t *out5) {
+  if (ctx && !ctx->children.empty())
+    return vr_debug_work_counters(ctx->children[0], out5);
   if (!ctx || !out5)
     return VR_ERR_ARGUMENT;
   if (!ctx->countWork)
@@ -1310,6 +1669,8 @@ int vr_debug_work_counters(vr_ctx *ctx, uint64_t *out5) {
 }
 
 int vr_debug_l2_read_bandwidth(vr_ctx *ctx, uint64_t bytes, int passes, double *out2) {
+  if (ctx && !ctx->children.empty())
+    return vr_debug_l2_read_bandwidth(ctx->children[0], bytes, passes, out2);
   if (!ctx || !out2 || bytes < 16 || passes < 1)
     return VR_ERR_ARGUMENT;
   CK(cudaSetDevice(ctx->device));

@@ -90,7 +90,13 @@ __device__ __noinline__ uint4 philoxBlock(uint32_t k0, uint32_t k1, uint32_t c0,
 }
 
 // Per-ray stream; replaces RNG rngState(tea<3>(idx, seed)),
-// rayTraceKernel.hpp:120-121.  The four-word buffer is shifted instead of
+// rayTraceKernel.hpp:120-121.  The stream is consumed block-aligned per ray segment: the
+// source sample starts at block 0 and the processing of every traced segment's hit
+// (rayTraceKernel.hpp:169-333: scatter test, reflection, roulette) starts at a fresh block,
+// unused words of the previous block are dropped (the oracle does the same, rng_discard).
+// So the state that travels with a ray between kernels is the block counter alone, and the
+// lanes of a warp that reflect generate their block at one common point instead of
+// wherever their buffers happen to run dry.  The four-word buffer is shifted instead of
 // indexed so it stays in registers.
 struct Rng {
   uint32_t k0, k1, c0, c1, blk;
@@ -104,32 +110,36 @@ struct Rng {
     blk = 0;
     left = 0;
   }
-  // state that survives between kernels: at most three buffered words
-  __device__ __forceinline__ uint4 save() const {
-    return make_uint4(b0, b1, b2, blk | ((uint32_t)left << 30));
-  }
-  __device__ __forceinline__ void load(uint4 s, uint32_t seed, uint32_t stream, uint64_t idx) {
+  // state that survives between kernels: the next block (a block generated ahead of its
+  // first draw -- refill() at the common point of a warp's reflecting lanes -- and then
+  // not touched, left == 4, is handed back: generating ahead never changes the stream)
+  __device__ __forceinline__ uint32_t save() const { return left == 4 ? blk - 1u : blk; }
+  __device__ __forceinline__ void load(uint32_t nextBlock, uint32_t seed, uint32_t stream,
+                                       uint64_t idx) {
     k0 = seed;
     k1 = stream;
     c0 = (uint32_t)idx;
     c1 = (uint32_t)(idx >> 32);
-    b0 = s.x;
-    b1 = s.y;
-    b2 = s.z;
-    b3 = 0u;
-    blk = s.w & 0x3fffffffu;
-    left = (int)(s.w >> 30);
+    blk = nextBlock;
+    left = 0;
+  }
+  __device__ __forceinline__ void discard() {
+    if (left == 4)
+      --blk;
+    left = 0;
+  }
+  __device__ __forceinline__ void refill() {
+    const uint4 o = philoxBlock(k0, k1, c0, c1, blk);
+    b0 = o.x;
+    b1 = o.y;
+    b2 = o.z;
+    b3 = o.w;
+    ++blk;
+    left = 4;
   }
   __device__ __forceinline__ uint32_t u32() {
-    if (left == 0) {
-      const uint4 o = philoxBlock(k0, k1, c0, c1, blk);
-      b0 = o.x;
-      b1 = o.y;
-      b2 = o.z;
-      b3 = o.w;
-      ++blk;
-      left = 4;
-    }
+    if (left == 0)
+      refill();
     uint32_t r = b0;
     b0 = b1;
     b1 = b2;
@@ -348,18 +358,8 @@ __device__ __forceinline__ bool checkLocal(const float4 P, const float4 N, const
     return false;
   float hx = (org.x + dir.x * tt) - P.x, hy = (org.y + dir.y * tt) - P.y,
         hz = (org.z + dir.z * tt) - P.z;
-  // radius > sqrtf(d2), decided without the square root unless d2 lies within 1e-5 of r^2
-  // (relative): d2 < fl(r2 * 0.99999) < r^2 (1 - 9e-6) gives sqrt_rn(d2) < r, and the mirror
-  // image for the other side; a radius whose square leaves the normal range takes the
-  // square root.  Same decision as the reference's comparison in every case.
-  const float d2 = dot3(hx, hy, hz, hx, hy, hz), r2 = P.w * P.w;
-  if (r2 > 1e-30f) {
-    if (d2 < r2 * 0.99999f)
-      return true;
-    if (d2 > r2 * 1.00001f)
-      return false;
-  }
-  return P.w > sqrtf(d2);
+  float distance = sqrtf(dot3(hx, hy, hz, hx, hy, hz));
+  return P.w > distance;
 }
 
 // checkLocalIntersection with the impact distance handed out (WDIST)

@@ -70,17 +70,25 @@ struct DeviceScene {
   int firstDir, secondDir;
   int bc[2];
   float btri[8][3][3];  // 8 triangles x 3 vertices
+  // constants of the closed-form boundary test (vr_trace.cu, boundaryTest), per lateral
+  // axis pair e (0: firstDir, triangles 0-3; 1: secondDir, triangles 4-7): the plane normal
+  // axis a and its cyclic successors b, c; Lb = fl(hi_b - lo_b), Lc likewise, P = fl(Lc * Lb)
+  struct {
+    int a, b, c;
+    float Lb, Lc, P;
+  } bnd[2];
 };
 
 // Resident pool of rays in flight (structure of arrays, one slot per ray).
-// The traverse kernel reads od0/od1 and writes hit; the shade kernel owns the
-// rest.  A slot with dir.x = NaN is empty.
+// The traverse kernel reads od0/od1, starts from hit (the ray's boundary hit, found by the
+// shade kernel -- or "none", hit.w = 1, for a ray fresh from the source) and writes the
+// closest hit back; the shade kernel owns the rest.  A slot with dir.x = NaN is empty.
 struct RayPool {
   uint32_t capacity;
   float4 *od0;   // org.x, org.y, org.z, dir.x
   float2 *od1;   // dir.y, dir.z
   float4 *hit;   // t, prim (bits), geom (bits), -
-  uint4 *rng;    // b0, b1, b2, blk | left << 30
+  uint32_t *rng; // next block of the ray's Philox stream (vr_device.cuh, struct Rng)
   uint4 *meta;   // idx lo, idx hi, numReflections, boundaryHits | hitFromBack << 31
   float *weight;
   float4 *dir3;  // particle-facing direction (differs from the ray's in 2D only)
@@ -93,6 +101,11 @@ struct TraceParams {
   int compact;      // 0: survivors stay in place; 1: append to poolOut
   vr_source_desc src;
   vr_particle_desc particle;
+  // sticking by material (device copies): matId[internal primitive], matSticking[numMaterials];
+  // matSticking == nullptr: the particle's constant sticking
+  const int *matId;
+  const float *matSticking;
+  int numMaterials;
   float ee;      // 1 / (sourcePower + 1), raySourceRandom.hpp:21
   float eeGrid;  // 2 / (sourcePower + 1), raySourceGrid.hpp:21
   const float *grid;  // grid source origins (n x 3) or null
@@ -156,9 +169,9 @@ cudaError_t buildNeighborsDevice(int D, const float *pts, uint32_t n, const floa
                                  float distance, uint32_t *offOut, uint32_t **idxOut,
                                  size_t *totalOut, cudaStream_t s);
 
-// flux of one particle: fixed point (internal order) -> float, optional SOURCE
+// flux of one particle: fixed point (ORIGINAL order, see vr_flux_device) -> float, optional SOURCE
 // normalisation by areas[original id], optional neighbour smoothing, original order
-cudaError_t postprocessFlux(const DeviceScene &sc, const unsigned long long *fixed,
+cudaError_t postprocessFlux(const DeviceScene &sc, const unsigned long long *fixedOrig,
                             const uint32_t *s2o, const float *areas, float normFactor, int smooth,
                             float *tmpA, float *tmpB, float *outOrig, cudaStream_t s);
 

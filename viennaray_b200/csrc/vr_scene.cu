@@ -313,14 +313,17 @@ __global__ void nbScanKernel(const float *pts, uint32_t n, NbGrid g, const unsig
 // ---- flux post-processing (rayTraceDisk.hpp:103-193, rayTraceTriangle.hpp:92-130) ----
 // internal (BVH) order in, float out.  f = (float)(fixed / 2^30); SOURCE
 // normalisation: f *= normFactor / area[original id]
-__global__ void fluxToFloatKernel(const unsigned long long *fixed, const uint32_t *s2o,
+// fixedOrig: the result words in the caller's primitive order (what vr_flux_device hands
+// out and a multi-GPU caller all-reduces); out: internal order, for the smoothing pass
+__global__ void fluxToFloatKernel(const unsigned long long *fixedOrig, const uint32_t *s2o,
                                   const float *areas, float normFactor, uint32_t n, float *out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
-  float f = (float)((double)fixed[i] * (1.0 / 1073741824.0));
+  const uint32_t o = s2o[i];
+  float f = (float)((double)fixedOrig[o] * (1.0 / 1073741824.0));
   if (areas)
-    f *= normFactor / areas[s2o[i]];
+    f *= normFactor / areas[o];
   out[i] = f;
 }
 
@@ -413,11 +416,11 @@ cudaError_t buildNeighborsDevice(int D, const float *pts, uint32_t n, const floa
   return cudaSuccess;
 }
 
-cudaError_t postprocessFlux(const DeviceScene &sc, const unsigned long long *fixed,
+cudaError_t postprocessFlux(const DeviceScene &sc, const unsigned long long *fixedOrig,
                             const uint32_t *s2o, const float *areas, float normFactor, int smooth,
                             float *tmpA, float *tmpB, float *outOrig, cudaStream_t s) {
   const uint32_t n = sc.numPrims;
-  fluxToFloatKernel<<<(n + 255) / 256, 256, 0, s>>>(fixed, s2o, areas, normFactor, n, tmpA);
+  fluxToFloatKernel<<<(n + 255) / 256, 256, 0, s>>>(fixedOrig, s2o, areas, normFactor, n, tmpA);
   const float *cur = tmpA;
   if (smooth && sc.geoType == 0) {
     smoothFluxKernel<<<(n + 255) / 256, 256, 0, s>>>(sc, tmpA, tmpB);
