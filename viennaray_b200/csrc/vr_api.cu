@@ -32,6 +32,8 @@ struct NcclApi {
 };
 static const int VR_NCCL_UINT64 = 5, VR_NCCL_SUM = 0;  // ncclUint64, ncclSum (nccl.h)
 
+#define VR_STAGE_CHUNK ((size_t)8 << 20)  // bytes of one pinned staging chunk (two per context)
+
 struct vr_ctx {
   // A multi-device context (vr_ctx_create_multi) is a parent that owns one ordinary context
   // per device: scene calls are replicated, a trace shards the ray-index range over the
@@ -42,6 +44,8 @@ struct vr_ctx {
   NcclApi nccl;
   int device = 0;
   int numSMs = 0;
+  char *hStage = nullptr;  // pinned staging of the uploads (stagedCopy), allocated on first use
+  cudaEvent_t stageEv[2] = {nullptr, nullptr};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -167,12 +171,48 @@ static void freeInputs(vr_ctx *c) {
   c->dTris = c->dNbOffO = c->dNbIdxO = nullptr;
   c->nbTotal = 0;
 }
+// Host -> device copy of a caller array.  The caller's memory is pageable; large arrays go
+// through two pinned staging chunks owned by the context, so that the CPU copy of one chunk
+// overlaps the DMA of the other and several contexts (one per GPU) uploading at once do not
+// queue behind the driver's own staging buffer.
+static cudaError_t stagedCopy(vr_ctx *c, void *dst, const void *src, size_t bytes) {
+  const size_t CH = VR_STAGE_CHUNK;
+  if (bytes < (1u << 20))
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+  if (!c->hStage) {
+    cudaError_t e = cudaMallocHost(&c->hStage, 2 * CH);
+    if (e == cudaSuccess)
+      e = cudaEventCreateWithFlags(&c->stageEv[0], cudaEventDisableTiming);
+    if (e == cudaSuccess)
+      e = cudaEventCreateWithFlags(&c->stageEv[1], cudaEventDisableTiming);
+    if (e != cudaSuccess)
+      return e;
+  }
+  size_t off = 0;
+  int k = 0;
+  while (off < bytes) {
+    const size_t m = std::min(CH, bytes - off);
+    cudaError_t e = cudaEventSynchronize(c->stageEv[k]);  // the chunk's previous DMA is done
+    if (e != cudaSuccess)
+      return e;
+    memcpy(c->hStage + (size_t)k * CH, (const char *)src + off, m);
+    e = cudaMemcpyAsync((char *)dst + off, c->hStage + (size_t)k * CH, m, cudaMemcpyHostToDevice,
+                        c->stream);
+    if (e == cudaSuccess)
+      e = cudaEventRecord(c->stageEv[k], c->stream);
+    if (e != cudaSuccess)
+      return e;
+    off += m;
+    k ^= 1;
+  }
+  return cudaSuccess;
+}
 // stream-ordered upload of a caller array into a fresh device buffer
 template <class T>
 static cudaError_t uploadArray(vr_ctx *c, T **dst, const T *src, size_t count) {
   cudaError_t e = cudaMallocAsync((void **)dst, sizeof(T) * std::max<size_t>(count, 1), c->stream);
   if (e == cudaSuccess && count)
-    e = cudaMemcpyAsync(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream);
+    e = stagedCopy(c, *dst, src, sizeof(T) * count);
   return e;
 }
 static void freeResults(vr_ctx *c) {
@@ -464,6 +504,10 @@ void vr_ctx_destroy(vr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
   }
   freeResults(ctx);
+  cudaFreeHost(ctx->hStage);
+  for (auto &e : ctx->stageEv)
+    if (e)
+      cudaEventDestroy(e);
   cudaFree(ctx->dCursor);
   cudaFree(ctx->dSlotCursor);
   cudaFree(ctx->dCounterCopies);
@@ -747,18 +791,6 @@ int vr_scene_set_boundary(vr_ctx *ctx, const float bboxMin[3], const float bboxM
         s.btri[i][k][a] = v[planes[firstDir][i][k]][a];
         s.btri[i + 4][k][a] = v[planes[secondDir][i][k]][a];
       }
-  for (int e = 0; e < 2; ++e) {
-    const int a = e ? secondDir : firstDir, b = (a + 1) % 3, c = (a + 2) % 3;
-    s.bnd[e].a = a;
-    s.bnd[e].b = b;
-    s.bnd[e].c = c;
-    // the float differences / product testTri forms from the vertices above
-    const volatile float Lb = s.bbox[1][b] - s.bbox[0][b], Lc = s.bbox[1][c] - s.bbox[0][c];
-    const volatile float P = Lc * Lb;
-    s.bnd[e].Lb = Lb;
-    s.bnd[e].Lc = Lc;
-    s.bnd[e].P = P;
-  }
   ctx->boundarySet = true;
   return VR_OK;
 }
@@ -1322,7 +1354,7 @@ int vr_flux_postprocess(vr_ctx *ctx, int particle, const float *areas, float nor
   CK(cudaMallocAsync(&buf, sizeof(float) * 4 * n, ctx->stream));
   cudaError_t e = cudaSuccess;
   if (areas)
-    e = cudaMemcpyAsync(buf, areas, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream);
+    e = stagedCopy(ctx, buf, areas, sizeof(float) * n);
   if (e == cudaSuccess)
     e = postprocessFlux(ctx->scene, ctx->dFluxOrig + (size_t)particle * n, ctx->bvh.sortedToOrig,
                         areas ? buf : nullptr, normFactor, smooth, buf + n, buf + 2 * n,

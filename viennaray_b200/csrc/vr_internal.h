@@ -70,19 +70,12 @@ struct DeviceScene {
   int firstDir, secondDir;
   int bc[2];
   float btri[8][3][3];  // 8 triangles x 3 vertices
-  // constants of the closed-form boundary test (vr_trace.cu, boundaryTest), per lateral
-  // axis pair e (0: firstDir, triangles 0-3; 1: secondDir, triangles 4-7): the plane normal
-  // axis a and its cyclic successors b, c; Lb = fl(hi_b - lo_b), Lc likewise, P = fl(Lc * Lb)
-  struct {
-    int a, b, c;
-    float Lb, Lc, P;
-  } bnd[2];
 };
 
 // Resident pool of rays in flight (structure of arrays, one slot per ray).
 // The traverse kernel reads od0/od1, starts from hit (the ray's boundary hit, found by the
-// shade kernel -- or "none", hit.w = 1, for a ray fresh from the source) and writes the
-// closest hit back; the shade kernel owns the rest.  A slot with dir.x = NaN is empty.
+// shade / init kernel) and writes the closest hit back; the shade kernel owns the rest.
+// A slot with dir.x = NaN is empty.
 struct RayPool {
   uint32_t capacity;
   float4 *od0;   // org.x, org.y, org.z, dir.x

@@ -55,16 +55,6 @@ namespace vr {
 #ifndef VR_SMEM_STACK
 #define VR_SMEM_STACK 0
 #endif
-// the per-ray work counters of shadeHit (neighbour tests, flux adds, sky exits; reported with
-// VR_COUNT_WORK=1) cost three registers in a kernel that is short of them
-#ifndef VR_WORK_COUNTERS
-#define VR_WORK_COUNTERS 1
-#endif
-#if VR_WORK_COUNTERS
-#define VR_WORK(x) x
-#else
-#define VR_WORK(x)
-#endif
 #define VR_WDIST_CAP 64  // disks one ray can hit at once (hit disk + its neighbour list)
 #ifndef VR_SHADE_BLOCKS_Q
 #define VR_SHADE_BLOCKS_Q 4
@@ -84,11 +74,7 @@ __device__ __forceinline__ bool slotEmpty(const float4 &od0) { return od0.w != o
 // places, and eight inlined triangle tests per call site pushed that kernel to
 // 123 KB of SASS (instruction-fetch stalls were 23 % of its samples).
 // (arguments and result by value: a real call that keeps everything in registers)
-#ifndef VR_BOUNDARY_GENERIC
-#define VR_BOUNDARY_GENERIC 0  // 1: the generic triangle tests below instead of boundaryTest's
-                               // closed form (kept for A/B checks; same results)
-#endif
-__device__ __noinline__ Hit boundaryTestGeneric(const DeviceScene &sc, const V3 org, const V3 dir) {
+__device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, const V3 dir) {
   Hit best;
   best.t = 3.402823466e+38f;
   best.geom = best.prim = best.orig = VR_INVALID_ID;
@@ -156,88 +142,7 @@ __device__ __noinline__ Hit boundaryTestGeneric(const DeviceScene &sc, const V3 
   return best;
 }
 
-// The same closest hit in closed form.  The eight boundary triangles are axis aligned and
-// their vertex table is fixed (Boundary::initBoundary, rayBoundary.hpp:182-233), so the
-// Moeller-Trumbore expressions of testTri collapse: with (a, b, c) the cyclic axes of a
-// plane normal to a, L_b / L_c the box extents, P = fl(L_c L_b) and C = v0 - org, v0 the
-// all-low (planes 0, 1 of an axis pair) or all-high (planes 2, 3) corner,
-//     Ng = (+-P, 0, 0)        den = +-fl(P d_a)       T = +-fl(P C_a)
-//     A1 = fl(R_b L_b)   A2 = fl(R_c L_c)   S = fl(A1 + A2)      R = cross(C, dir)
-//     low plane:   triangle 0: (U, V) = ( S, -A1)    triangle 1: (U, V) = ( A2, -S)
-//     high plane:  triangle 2: (U, V) = (-S,  A2)    triangle 3: (U, V) = (-A1,  S)
-// (every other term of the dot products is a product with an exact zero; adding +-0 changes
-// nothing, and the comparisons do not see the sign of a zero).  These are the very float
-// operations testTri performs on those vertices, so hit / miss, t and the winning triangle
-// are bit-identical -- the parity suite runs both (VR_BOUNDARY_GENERIC) -- at about a third
-// of the instructions.  sc.bnd holds the per-axis constants (vr_scene_set_boundary).
-__device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, const V3 dir) {
-#if VR_BOUNDARY_GENERIC
-  return boundaryTestGeneric(sc, org, dir);
-#else
-  Hit best;
-  best.t = 3.402823466e+38f;
-  best.geom = best.prim = best.orig = VR_INVALID_ID;
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int a = sc.bnd[e].a, b = sc.bnd[e].b, c = sc.bnd[e].c;
-    const float da = comp(dir, a);
-    const float q = sc.bnd[e].P * da;  // den = +-q
-    if (q == 0.f)
-      continue;
-    const float oa = comp(org, a);
-    // only a plane on the side the ray moves towards can give T > 0: C_a and d_a of one sign
-    const float CaLo = sc.bbox[0][a] - oa, CaHi = sc.bbox[1][a] - oa;
-    const bool pos = da > 0.f;
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const float Ca = side ? CaHi : CaLo;
-      if (!(pos ? Ca > 0.f : Ca < 0.f))
-        continue;
-      const float Cb = sc.bbox[side][b] - comp(org, b), Cc = sc.bbox[side][c] - comp(org, c);
-      const float db = comp(dir, b), dc = comp(dir, c);
-      const float Rb = Cc * da - Ca * dc, Rc = Ca * db - Cb * da;
-      const float A1 = Rb * sc.bnd[e].Lb, A2 = Rc * sc.bnd[e].Lc;
-      const float S = A1 + A2;
-      float den = side ? -q : q;
-      float T = sc.bnd[e].P * Ca;
-      if (side)
-        T = -T;
-      // (U, V) of the plane's two triangles, then the sign flip of testTri for den < 0
-      float U0 = side ? -S : S, V0 = side ? A2 : -A1;
-      float U1 = side ? -A1 : A2, V1 = side ? S : -S;
-      if (den < 0.f) {
-        U0 = -U0;
-        V0 = -V0;
-        U1 = -U1;
-        V1 = -V1;
-        T = -T;
-      }
-      const float absDen = fabsf(den);
-      if (!(absDen * VR_TNEAR < T && T <= absDen * 3.402823466e+38f))
-        continue;
-      const bool h0 = U0 >= 0.f && V0 >= 0.f && U0 + V0 <= absDen;
-      const bool h1 = U1 >= 0.f && V1 >= 0.f && U1 + V1 <= absDen;
-      if (!(h0 || h1))
-        continue;
-      const float t = T / absDen;
-      const uint32_t prim = (uint32_t)(4 * e + 2 * side) + (h0 ? 0u : 1u);  // lower index on a tie
-      if (better(t, 0u, prim, best)) {
-        best.t = t;
-        best.geom = 0u;
-        best.prim = best.orig = prim;
-      }
-    }
-  }
-  return best;
-#endif
-}
-
-// hit record of a ray fresh from the source: no boundary hit looked for yet (w = 1)
-__device__ __forceinline__ float4 lazyHit() {
-  return make_float4(3.402823466e+38f, __uint_as_float(VR_INVALID_ID),
-                     __uint_as_float(VR_INVALID_ID), 1.f);
-}
-// closest boundary hit of a ray that goes on, stored as the traversal's initial best
+// closest boundary hit of a fresh ray, stored as the traversal's initial best
 __device__ __forceinline__ void storeBoundaryHit(const DeviceScene &sc, const RayPool &pool,
                                                  uint32_t s, const V3 &org, const V3 &dir) {
   const Hit best = boundaryTest(sc, org, dir);
@@ -486,7 +391,6 @@ __global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
   uint32_t stack[VR_STACK];
   int sp = 0;
   bool exhausted = false;
-  float mark = 0.f;
   unsigned wNodes = 0, wPrims = 0;
 
   for (;;) {
@@ -511,15 +415,11 @@ __global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
             org = {a.x, a.y, a.z};
             dir = {a.w, b.x, b.y};
             nr = makeNodeRay(sc, org, dir);
-            // the slot's hit is the traversal's initial best: the boundary hit the shade
-            // kernel already found for a ray that goes on, or "none" (t = max) for a ray
-            // fresh from the source, whose boundary hit is only looked for if its traversal
-            // shows that it can have met the box (hit.w marks those, and is kept)
+            // the shade / init kernel already intersected the boundary box
             const float4 h0 = __ldcs(&p.pool.hit[s]);
             best.t = h0.x;
             best.prim = best.orig = __float_as_uint(h0.y);
             best.geom = __float_as_uint(h0.z);
-            mark = h0.w;
             sp = 0;
             cur = sc.numPrims ? (TOP ? VR_TOP_BASE : sc.rootRef) : VR_DONE;
           }
@@ -655,7 +555,7 @@ __global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
     // ---- finished: publish the hit, free the lane ---------------------------------
     if (slot != VR_INVALID_ID && cur == VR_DONE) {
       __stcs(&p.pool.hit[slot], make_float4(best.t, __uint_as_float(best.prim),
-                                            __uint_as_float(best.geom), mark));
+                                            __uint_as_float(best.geom), 0.f));
       slot = VR_INVALID_ID;
     }
   }
@@ -840,7 +740,7 @@ template <int D> __global__ void __launch_bounds__(256) initPoolKernel(const Tra
     return;
   if (ok) {
     storeRay<D>(p.pool, s, org, dir, rd, 1.f, rng, idx, 0u, 0u, false);
-    __stcs(&p.pool.hit[s], lazyHit());
+    storeBoundaryHit(p.scene, p.pool, s, org, dir);
   } else {
     p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
   }
@@ -868,72 +768,49 @@ struct RayState {
   uint64_t idx;
   uint32_t numReflections, boundaryHits;
   bool hitFromBack;
-  bool bhValid;  // bh is the boundary hit of the ray as it stands after shadeHit (it goes on)
+  bool rngLoaded;  // rng holds the ray's stream (else it still sits in rs as loaded from the pool)
+  bool bhValid;    // bh is the boundary hit of the ray as it stands after the call
   Hit bh;
-  Rng rng;  // loaded with the ray's next block; draws refill it
+  Rng rng;
+  uint32_t rs;  // the ray's next Philox block as loaded from the pool
 };
 struct Tally {
   unsigned cTraces, cMiss, cGeo, cBnd, cRefl, cTerm, wNb, wFlux, wSky, cScatter;
 };
 
-// What rayTraceKernel.hpp:169-333 does with the hit of a ray: miss, boundary handling,
-// back-face rule, neighbour spread, particle functor, roulette, and the sky map's shortcut
-// for rays that leave the scene.  Returns true when the ray ended.
-//
-// (ht, hprim, hgeom) is the closest hit over the geometry and the boundary box -- or, for a
-// ray fresh from the source (`lazy`), over the geometry alone: such a ray starts on the
-// source plane inside the box and nearly always ends on the surface below it, so its
-// boundary hit is only looked for here when the traversal's result says that it can have met
-// the box at all (a miss, or origin / hit point not well inside the lateral planes; the box
-// is convex).  A boundary hit no farther than the geometry hit wins (lower geomID on a tie,
-// the oracle's rule).  A ray that goes on leaves with its next boundary hit in r.bh: one
-// boundaryTest call site serves every such lane of the warp.
-//
-// EXT == 1 adds the two optional features that are off in the default
-// instantiation: mean-free-path scattering (rayTraceKernel.hpp:179-203) and the
-// distance-weighted neighbour spread of VIENNARAY_USE_WDIST (:258-296).
+// What rayTraceKernel.hpp:169-333 does with the hit (t, prim, geom) of a ray: miss,
+// boundary handling, back-face rule, neighbour spread, particle functor, roulette, and
+// the sky map's shortcut for rays that leave the scene.  Returns true when the ray ended.
+// EXT == 1 adds the optional features that are off in the default instantiation:
+// mean-free-path scattering (rayTraceKernel.hpp:179-203), the distance-weighted neighbour
+// spread of VIENNARAY_USE_WDIST (:258-296) and sticking looked up by the hit primitive's
+// materialId (:310-313).
 template <int D, int GEO, int EXT, int Q>
-__device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, float ht,
-                                         uint32_t hprim, uint32_t hgeom, bool lazy, Tally &c) {
+__device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, const float ht,
+                                         const uint32_t hprim, const uint32_t hgeom, Tally &c) {
   const DeviceScene &sc = p.scene;
   V3 &org = r.org, &dir = r.dir, &rayDirection = r.rayDirection;
   float &w = r.w;
+  const uint64_t idx = r.idx;
   uint32_t &numReflections = r.numReflections, &boundaryHits = r.boundaryHits;
-  bool &hitFromBack = r.hitFromBack;
+  bool &hitFromBack = r.hitFromBack, &rngLoaded = r.rngLoaded, &bhValid = r.bhValid;
+  Hit &bh = r.bh;
   Rng &rng = r.rng;
+  const uint32_t rs = r.rs;
   unsigned &cTraces = c.cTraces, &cMiss = c.cMiss, &cGeo = c.cGeo, &cBnd = c.cBnd,
            &cRefl = c.cRefl, &cTerm = c.cTerm, &wNb = c.wNb, &wFlux = c.wFlux, &wSky = c.wSky,
            &cScatter = c.cScatter;
   bool finish = false;
-  bool reflected = false;
-  r.bhValid = false;
+  bhValid = false;
   ++cTraces;
-  rng.discard();  // this segment's draws start at a fresh block
-  // ---- the boundary box of a ray that was traversed without its boundary hit ------------
-  if (lazy) {
-    bool needBox = hgeom == VR_INVALID_ID || D == 2;
-    if (!needBox) {
-      const int a0 = sc.firstDir, a1 = sc.secondDir;
-      const float m0 = 1e-3f * (sc.bbox[1][a0] - sc.bbox[0][a0]),
-                  m1 = 1e-3f * (sc.bbox[1][a1] - sc.bbox[0][a1]);
-      const float o0 = comp(org, a0), o1 = comp(org, a1);
-      const float h0 = o0 + comp(dir, a0) * ht, h1 = o1 + comp(dir, a1) * ht;
-      const bool inside = fminf(o0, h0) > sc.bbox[0][a0] + m0 &&
-                          fmaxf(o0, h0) < sc.bbox[1][a0] - m0 &&
-                          fminf(o1, h1) > sc.bbox[0][a1] + m1 && fmaxf(o1, h1) < sc.bbox[1][a1] - m1;
-      needBox = !inside;
-    }
-    if (needBox) {
-      const Hit bh = boundaryTest(sc, org, dir);
-      if (bh.geom == 0u && !(hgeom != VR_INVALID_ID && ht < bh.t)) {
-        hgeom = 0u;
-        hprim = bh.prim;
-        ht = bh.t;
-      }
-    }
-  }
+  if (rngLoaded)
+    rng.discard();  // (tail kernel) this segment's draws start at a fresh block
   bool scattered = false;
   if (EXT && hgeom != VR_INVALID_ID && p.particle.meanFreePath > 0.f) {  // :179-203
+    if (!rngLoaded) {
+      rng.load(rs, p.seed, p.stream, idx);
+      rngLoaded = true;
+    }
     const float scatterProbability =
         1.f - exp2det((-ht / p.particle.meanFreePath) * 1.4426950216293335f);
     const float rnd = rng.f();
@@ -997,7 +874,7 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, floa
           float4 P, Nn;
           ldg256(&sc.prim[2 * id], P, Nn);
           float dd;
-          VR_WORK(++wNb;)
+          ++wNb;
           if (checkLocalDist(P, Nn, org, dir, dd) && nh < VR_WDIST_CAP) {
             ids[nh] = id;
             dist[nh++] = dd + 1e-6f;
@@ -1008,7 +885,7 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, floa
           invSum += 1.f / dist[k];
         for (uint32_t k = 0; k < nh; ++k) {
           atomicAdd(&p.flux[ids[k]], toFixed(((w / dist[k]) / invSum) * (float)nh));
-          VR_WORK(++wFlux;)
+          ++wFlux;
         }
       } else if (Q) {
         // :271-306 handed to spreadKernel: {org, weight}, {dir, hit disk}
@@ -1018,7 +895,7 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, floa
       } else {
         const unsigned long long wf = toFixed(w);
         atomicAdd(&p.flux[hprim], wf);  // :297-306 surfaceCollision
-        VR_WORK(++wFlux;)
+        ++wFlux;
         if (GEO == 0) {  // :271-280 neighbour spread
           const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
           // four neighbours per round: all index loads, then all disk loads,
@@ -1036,21 +913,26 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, floa
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (id[j] != VR_INVALID_ID) {
-                VR_WORK(++wNb;)
+                ++wNb;
                 if (checkLocal(P[j], Nn[j], org, dir)) {
                   atomicAdd(&p.flux[id[j]], wf);
-                  VR_WORK(++wFlux;)
+                  ++wFlux;
                 }
               }
           }
         }
       }
-      // every reflecting lane of the warp generates its block here, side by side
+      if (!rngLoaded) {
+        rng.load(rs, p.seed, p.stream, idx);
+        rngLoaded = true;
+      }
+      // every reflecting lane of the warp generates its block here, side by side (a block
+      // that ends up unused is handed back: Rng::save / discard)
       if (rng.left == 0)
         rng.refill();
       const V3 newDir = surfaceReflection<D>(p.particle, rayDirection, gn, rng);  // :310
       float sticking = p.particle.sticking;
-      if (p.matSticking) {  // sticking by the materialId of the hit primitive, :310-313
+      if (EXT && p.matSticking) {  // sticking by the materialId of the hit primitive, :310-313
         const int m = __ldg(&p.matId[hprim]);
         if (m >= 0 && m < p.numMaterials)
           sticking = __ldg(&p.matSticking[m]);
@@ -1074,38 +956,35 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, floa
           rayDirection = newDir;
           org = hitPoint;
           dir = fillDir<D>(rayDirection);
-          reflected = true;
         }
       }
-    }
-  }
-  // ---- every ray that goes on: its next boundary hit (the one call site of the warp) ----
-  if (!finish) {
-    r.bh = boundaryTest(sc, org, dir);
-    r.bhValid = true;
-    if (D == 3 && reflected && sc.sky != nullptr &&
-        !(EXT && p.particle.meanFreePath > 0.f)) {  // the boundary walk would need the scatter draws
-      // if the sky map proves that the reflected ray meets no primitive, walk it through
-      // the boundary conditions to its end right here: it never needs a traversal
-      if (skyEscapes(sc, org, dir, r.bh.t)) {
-        VR_WORK(++wSky;)
-        for (;;) {
-          ++cTraces;
-          if (r.bh.geom == VR_INVALID_ID) {
-            ++cMiss;
-            finish = true;
-            break;
+      if (D == 3 && !finish && sc.sky != nullptr &&
+          !(EXT && p.particle.meanFreePath > 0.f)) {  // the boundary walk would need the scatter draws
+        // boundary hit of the reflected ray (needed anyway); if the sky map proves
+        // that the ray meets no primitive, walk it through the boundary to its
+        // end right here: it never needs a traversal
+        bh = boundaryTest(sc, org, dir);
+        bhValid = true;
+        if (skyEscapes(sc, org, dir, bh.t)) {
+          ++wSky;
+          for (;;) {
+            ++cTraces;
+            if (bh.geom == VR_INVALID_ID) {
+              ++cMiss;
+              finish = true;
+              break;
+            }
+            if (++boundaryHits > p.maxBoundaryHits) {
+              ++cTerm;
+              finish = true;
+              break;
+            }
+            if (!boundaryHit<D>(sc, org, rayDirection, dir, bh.prim, bh.t)) {
+              finish = true;
+              break;
+            }
+            bh = boundaryTest(sc, org, dir);
           }
-          if (++boundaryHits > p.maxBoundaryHits) {
-            ++cTerm;
-            finish = true;
-            break;
-          }
-          if (!boundaryHit<D>(sc, org, rayDirection, dir, r.bh.prim, r.bh.t)) {
-            finish = true;
-            break;
-          }
-          r.bh = boundaryTest(sc, org, dir);
         }
       }
     }
@@ -1119,6 +998,7 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, floa
 
 template <int D, int GEO, int EXT, int Q>
 __global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) shadeKernel(const __grid_constant__ TraceParams p) {
+  const DeviceScene &sc = p.scene;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t numSlots = *p.slotCount;
 
@@ -1136,16 +1016,19 @@ __global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) 
   r.w = 0.f;
   r.idx = 0;
   r.numReflections = r.boundaryHits = 0u;
-  r.hitFromBack = r.bhValid = false;
+  r.hitFromBack = r.rngLoaded = r.bhValid = false;
   r.bh.t = 0.f;
   r.bh.geom = r.bh.prim = r.bh.orig = VR_INVALID_ID;
   r.rng.init(0, 0, 0);
+  r.rs = 0u;
   V3 &org = r.org, &dir = r.dir, &rayDirection = r.rayDirection;
   float &w = r.w;
   uint64_t &idx = r.idx;
   uint32_t &numReflections = r.numReflections, &boundaryHits = r.boundaryHits;
-  bool &hitFromBack = r.hitFromBack;
+  bool &hitFromBack = r.hitFromBack, &rngLoaded = r.rngLoaded, &bhValid = r.bhValid;
+  Hit &bh = r.bh;
   Rng &rng = r.rng;
+  uint32_t &rs = r.rs;
 
   if (live) {
     const float2 b = __ldcs(&p.pool.od1[s]);
@@ -1163,9 +1046,8 @@ __global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) 
     boundaryHits = meta.w & 0x7fffffffu;
     hitFromBack = (meta.w >> 31) != 0u;
     w = __ldcs(&p.pool.weight[s]);
-    rng.load(__ldcs(&p.pool.rng[s]), p.seed, p.stream, idx);
-    finish = shadeHit<D, GEO, EXT, Q>(p, r, hv.x, __float_as_uint(hv.y), __float_as_uint(hv.z),
-                                      hv.w != 0.f, c);
+    rs = __ldcs(&p.pool.rng[s]);  // issued with the other pool loads, not after the neighbour gathers
+    finish = shadeHit<D, GEO, EXT, Q>(p, r, hv.x, __float_as_uint(hv.y), __float_as_uint(hv.z), c);
   }
 
   // ---- regenerate finished slots; write survivors back (in place, or appended to
@@ -1180,17 +1062,22 @@ __global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) 
         __stcs(&p.pool.meta[s], make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
                                            boundaryHits | (hitFromBack ? 0x80000000u : 0u)));
         __stcs(&p.pool.weight[s], w);
-        __stcs(&p.pool.rng[s], rng.save());
+        if (rngLoaded)  // draws were taken from the stream
+          __stcs(&p.pool.rng[s], rng.save());
         if (D == 2)
           __stcs(&p.pool.dir3[s],
                  make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f));
-        __stcs(&p.pool.hit[s], make_float4(r.bh.t, __uint_as_float(r.bh.prim),
-                                           __uint_as_float(r.bh.geom), 0.f));
       } else if (regen) {
         storeRay<D>(p.pool, s, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
-        __stcs(&p.pool.hit[s], lazyHit());
       } else {
         p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
+      }
+      if (survive) {
+        if (!finish && bhValid)  // the boundary hit of this ray is known already
+          __stcs(&p.pool.hit[s], make_float4(bh.t, __uint_as_float(bh.prim),
+                                             __uint_as_float(bh.geom), 0.f));
+        else
+          storeBoundaryHit(sc, p.pool, s, org, dir);
       }
     }
   } else {
@@ -1205,14 +1092,18 @@ __global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) 
       if (survive) {
         const uint32_t dst = base + __popc(m & ((1u << ln) - 1u));
         if (!finish) {
+          if (!rngLoaded)
+            rng.load(rs, p.seed, p.stream, idx);
           storeRay<D>(p.poolOut, dst, org, dir, rayDirection, w, rng, idx, numReflections,
                       boundaryHits, hitFromBack);
-          __stcs(&p.poolOut.hit[dst], make_float4(r.bh.t, __uint_as_float(r.bh.prim),
-                                                  __uint_as_float(r.bh.geom), 0.f));
         } else {
           storeRay<D>(p.poolOut, dst, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
-          __stcs(&p.poolOut.hit[dst], lazyHit());
         }
+        if (!finish && bhValid)
+          __stcs(&p.poolOut.hit[dst], make_float4(bh.t, __uint_as_float(bh.prim),
+                                                  __uint_as_float(bh.geom), 0.f));
+        else
+          storeBoundaryHit(sc, p.poolOut, dst, org, dir);
       }
     }
   }
@@ -1294,7 +1185,7 @@ __global__ void __launch_bounds__(256) spreadKernel(const __grid_constant__ Trac
 
 cudaError_t launchSpread(const TraceParams &p, int numSMs, cudaStream_t s) {
   if (!p.spreadQ || p.numSlots == 0 || p.scene.geoType != 0 || p.scene.D != 3 ||
-      p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST))
+      p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST) || p.matSticking)
     return cudaSuccess;
   unsigned grid = (p.numSlots + 255u) / 256u;
   const unsigned cap = (unsigned)numSMs * 8u;
@@ -1329,27 +1220,30 @@ __global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ TraceP
     } else {
       r.rayDirection = r.dir;
     }
+    const float4 hv = __ldcs(&p.pool.hit[s]);
     const uint4 meta = __ldcs(&p.pool.meta[s]);
     r.idx = (uint64_t)meta.x | ((uint64_t)meta.y << 32);
     r.numReflections = meta.z;
     r.boundaryHits = meta.w & 0x7fffffffu;
     r.hitFromBack = (meta.w >> 31) != 0u;
     r.w = __ldcs(&p.pool.weight[s]);
-    r.rng.load(__ldcs(&p.pool.rng[s]), p.seed, p.stream, r.idx);
-    // the slot's hit: the ray's boundary hit, or none yet (hit.w: see traverseKernel)
-    const float4 hv = __ldcs(&p.pool.hit[s]);
-    bool lazy = hv.w != 0.f;
+    r.rs = __ldcs(&p.pool.rng[s]);
+    r.rngLoaded = false;
+    r.rng.init(0, 0, 0);
+    r.bhValid = true;  // the pool holds the ray's boundary hit
     r.bh.t = hv.x;
     r.bh.prim = r.bh.orig = __float_as_uint(hv.y);
     r.bh.geom = __float_as_uint(hv.z);
     for (;;) {
+      if (!r.bhValid)
+        r.bh = boundaryTest(sc, r.org, r.dir);
       Hit best = r.bh;
       traverseOne<GEO>(sc, r.org, r.dir, best, wNodes, wPrims);
-      if (shadeHit<D, GEO, EXT, 0>(p, r, best.t, best.prim, best.geom, lazy, c))
+      if (shadeHit<D, GEO, EXT, 0>(p, r, best.t, best.prim, best.geom, c))
         break;
-      lazy = false;  // a ray that goes on carries its boundary hit (r.bh)
     }
   }
+
   const unsigned lane = threadIdx.x & 31u;
   unsigned long long *cnt =
       p.counters + (size_t)((blockIdx.x * 4u + (threadIdx.x >> 5)) % VR_COUNTER_COPIES) * 8;
@@ -1390,7 +1284,7 @@ cudaError_t launchTail(const TraceParams &p, cudaStream_t s) {
   if (p.numSlots == 0)
     return cudaSuccess;
   const unsigned grid = (p.numSlots + 127u) / 128u;
-  if (p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST))
+  if (p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST) || p.matSticking)
     launchTailExt<1>(p, grid, s);
   else
     launchTailExt<0>(p, grid, s);
@@ -1445,7 +1339,7 @@ cudaError_t launchShade(const TraceParams &p, cudaStream_t s) {
   if (p.numSlots == 0)
     return cudaSuccess;
   const unsigned grid = (p.numSlots + 255u) / 256u;
-  if (p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST))
+  if (p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST) || p.matSticking)
     launchShadeExt<1>(p, grid, s);
   else
     launchShadeExt<0>(p, grid, s);
