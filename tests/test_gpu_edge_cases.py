@@ -189,3 +189,23 @@ def test_l2_read_bandwidth_diagnostic():
     with pytest.raises(capi.VrError):
         ctx.l2_read_bandwidth(0, 10)
     ctx.close()
+
+
+def test_long_neighbour_lists():
+    """A plane sampled four times denser than its disk radius asks for: every disk has far more
+    than the eight neighbours of the row format (vr_internal.h, nbRow), so the spread walks the
+    row and several rounds of the CSR behind it; both reflective boundaries are hit."""
+    from viennaray_b200 import scenes
+    p, n = scenes.plane_grid(0.125, 2.0)
+    c = dict(name="dense", D=3, geo="disk", points=p, normals=n, grid_delta=0.5, bc=[0, 0, 0],
+             source_dir=host.POS_Z, kind=0, sticking=0.5, power=1.0, cone=0.0)
+    st = common.product_setup(c)
+    counts = np.diff(st["nb"][0])
+    assert counts.max() > 20 and counts.min() >= 8
+    orc = common.make_oracle(c)
+    ctx, src, _ = common.make_gpu(c)
+    fo, io = orc.trace(common.oracle_particle(c), orc.config(30000, SEED))
+    ctx.trace_device(src, [common.gpu_particle(c)], host.config(30000, SEED), sync=True)
+    assert (ctx.flux_download_fixed()[0] == fo).all()
+    assert ctx.flux_download()[1][0].totalRaysTraced == io.totalTraces
+    ctx.close()

@@ -65,7 +65,7 @@ struct vr_ctx {
 
   // device scene (internal = BVH order)
   float4 *dPrim = nullptr;
-  uint32_t *dNbOff = nullptr, *dNbIdx = nullptr;
+  uint32_t *dNbOff = nullptr, *dNbIdx = nullptr, *dNbRow = nullptr;
   int *dMatId = nullptr;       // material IDs, internal order
   float *dMatTab = nullptr;    // sticking tables of the running trace (all particles)
   size_t matTabCap = 0;
@@ -149,10 +149,11 @@ static void freeDeviceScene(vr_ctx *c) {
   cudaFreeAsync(c->dPrim, c->stream);
   cudaFreeAsync(c->dNbOff, c->stream);
   cudaFreeAsync(c->dNbIdx, c->stream);
+  cudaFreeAsync(c->dNbRow, c->stream);
   cudaFreeAsync(c->dMatId, c->stream);
   c->dMatId = nullptr;
   c->dPrim = nullptr;
-  c->dNbOff = c->dNbIdx = nullptr;
+  c->dNbOff = c->dNbIdx = c->dNbRow = nullptr;
   freeBvh(&c->bvh, c->stream);
   cudaFreeAsync(c->dSky, c->stream);
   c->dSky = nullptr;
@@ -791,6 +792,21 @@ int vr_scene_set_boundary(vr_ctx *ctx, const float bboxMin[3], const float bboxM
         s.btri[i][k][a] = v[planes[firstDir][i][k]][a];
         s.btri[i + 4][k][a] = v[planes[secondDir][i][k]][a];
       }
+  // constants of the boundary test's shortcut.  The normal component is formed with the
+  // float operations of testTri (vr_device.cuh): e1 = v0 - v1, e2 = v2 - v0,
+  // Ng = cross(e2, e1); volatile keeps every intermediate a rounded float
+  s.bFast = (D == 3 && firstDir == 0 && secondDir == 1 && !getenv("VR_BOUNDARY_GENERIC")) ? 1 : 0;
+  s.bExt = std::max(std::max(s.bbox[1][0] - s.bbox[0][0], s.bbox[1][1] - s.bbox[0][1]),
+                    s.bbox[1][2] - s.bbox[0][2]);
+  for (int i = 0; i < 8; ++i) {
+    const int a = i < 4 ? firstDir : secondDir, b = (a + 1) % 3, c = (a + 2) % 3;
+    volatile float e1b = s.btri[i][0][b] - s.btri[i][1][b], e1c = s.btri[i][0][c] - s.btri[i][1][c];
+    volatile float e2b = s.btri[i][2][b] - s.btri[i][0][b], e2c = s.btri[i][2][c] - s.btri[i][0][c];
+    volatile float p1 = e2b * e1c, p2 = e2c * e1b;
+    volatile float na = p1 - p2;  // component a of cross(e2, e1)
+    s.bN[i] = na;
+    s.bX[i] = s.btri[i][0][a];
+  }
   ctx->boundarySet = true;
   return VR_OK;
 }
@@ -872,8 +888,9 @@ int vr_scene_commit(vr_ctx *ctx) {
   CKT(cudaMallocAsync(&ctx->dNbIdx, sizeof(uint32_t) * std::max<size_t>(ctx->nbTotal, 1), st));
   CKT(cudaMallocAsync(&o2s, sizeof(uint32_t) * n, st));
   CKT(cudaMallocAsync(&cnt, sizeof(uint32_t) * n, st));
+  CKT(cudaMallocAsync(&ctx->dNbRow, sizeof(uint32_t) * 8 * (size_t)n, st));
   CKT(remapNeighbors(ctx->bvh.sortedToOrig, ctx->dNbOffO, ctx->dNbIdxO, n, o2s, cnt, ctx->dNbOff,
-                     ctx->dNbIdx, st));
+                     ctx->dNbIdx, ctx->dNbRow, st));
   {  // material IDs into the internal (BVH) order
     int *matOrig = nullptr;
     CKT(uploadArray(ctx, &matOrig, ctx->materialIds.data(), (size_t)n));
@@ -899,6 +916,7 @@ int vr_scene_commit(vr_ctx *ctx) {
   }
   s.nbOff = ctx->dNbOff;
   s.nbIdx = ctx->dNbIdx;
+  s.nbRow = reinterpret_cast<const uint4 *>(ctx->dNbRow);
   s.nodes = ctx->bvh.nodes;
   s.nodes4 = ctx->bvh.nodes4;
   s.rootRef = ctx->bvh.rootRef;

@@ -51,6 +51,39 @@ __device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
                  "=r"(b.w)
                : "l"(p));
 }
+// tuning variants of the traverse kernel's loads (measured in DESIGN.md section 4): cache
+// policy of the node / disk records in L1 and prefetches into L1
+#ifndef VR_NODE_LD
+#define VR_NODE_LD 0  // 1: nodes with L1::evict_last
+#endif
+#ifndef VR_DISK_LD
+#define VR_DISK_LD 0  // 1: disks with L1::no_allocate, 2: L1::evict_first
+#endif
+__device__ __forceinline__ void prefetchL1(const void *p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void ldgNode(const void *p, uint4 &a, uint4 &b) {
+#if VR_NODE_LD == 1
+  asm volatile("ld.global.nc.L1::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z),
+                 "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void ldgDisk(const float4 *p, float4 &a, float4 &b) {
+#if VR_DISK_LD == 1
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif VR_DISK_LD == 2
+  asm volatile("ld.global.nc.L1::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z),
+                 "=f"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z),

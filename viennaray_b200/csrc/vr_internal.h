@@ -47,6 +47,9 @@ struct DeviceScene {
   const float4 *prim;
   const uint32_t *nbOff;  // neighbour CSR, internal indices
   const uint32_t *nbIdx;
+  // the first eight neighbours of every disk as one 32-byte row (2 x uint4, padded with
+  // VR_INVALID_ID); bit 31 of the eighth word: the CSR row continues at entry 8
+  const uint4 *nbRow;
   const Node2 *nodes;
   const uint4 *nodes4;  // optional 4-wide nodes or null
   uint32_t rootRef;
@@ -70,6 +73,13 @@ struct DeviceScene {
   int firstDir, secondDir;
   int bc[2];
   float btri[8][3][3];  // 8 triangles x 3 vertices
+  // shortcut of the boundary test (boundaryTest, vr_trace.cu): set when the lateral axes
+  // are x and y.  bN[i]: the one non-zero component of triangle i's unnormalised normal
+  // cross(v2 - v0, v0 - v1) as the triangle test computes it, bX[i]: v0's coordinate on
+  // the plane's axis, bExt: largest box extent (margin scale)
+  int bFast;
+  float bExt;
+  float bN[8], bX[8];
 };
 
 // Resident pool of rays in flight (structure of arrays, one slot per ray).
@@ -156,7 +166,7 @@ cudaError_t launchGatherPrims(int geoType, const float4 *A, const float4 *B, con
                               cudaStream_t s);
 cudaError_t remapNeighbors(const uint32_t *s2o, const uint32_t *offO, const uint32_t *idxO,
                            uint32_t n, uint32_t *o2s, uint32_t *cnt, uint32_t *off, uint32_t *idx,
-                           cudaStream_t s);
+                           uint32_t *row, cudaStream_t s);
 
 cudaError_t buildNeighborsDevice(int D, const float *pts, uint32_t n, const float lo[3],
                                  float distance, uint32_t *offOut, uint32_t **idxOut,

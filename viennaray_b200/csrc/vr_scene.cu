@@ -72,14 +72,32 @@ __global__ void invertAndCountKernel(const uint32_t *s2o, const uint32_t *offO, 
 
 __global__ void remapRowsKernel(const uint32_t *s2o, const uint32_t *o2s, const uint32_t *offO,
                                 const uint32_t *idxO, const uint32_t *off, uint32_t n,
-                                uint32_t *idx) {
+                                uint32_t *idx, uint32_t *row) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
-  const uint32_t o = s2o[i];
-  uint32_t w = off[i];
-  for (uint32_t k = offO[o]; k < offO[o + 1]; ++k)
-    idx[w++] = o2s[idxO[k]];
+  uint32_t first[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    first[j] = VR_INVALID_ID;
+  if (offO && idxO) {
+    const uint32_t o = s2o[i];
+    uint32_t w = off[i];
+    const uint32_t k0 = offO[o], k1 = offO[o + 1];
+    for (uint32_t k = k0; k < k1; ++k) {
+      const uint32_t id = o2s[idxO[k]];
+      idx[w++] = id;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (k - k0 == (uint32_t)j)
+          first[j] = id;
+    }
+    if (k1 - k0 > 8u)
+      first[7] |= 0x80000000u;  // the row continues in the CSR
+  }
+  uint4 *r = reinterpret_cast<uint4 *>(row) + 2 * (size_t)i;
+  r[0] = make_uint4(first[0], first[1], first[2], first[3]);
+  r[1] = make_uint4(first[4], first[5], first[6], first[7]);
 }
 
 // off[n] = off[n-1] + cnt[n-1] (the exclusive scan leaves the total out)
@@ -487,7 +505,7 @@ cudaError_t launchGatherPrims(int geoType, const float4 *A, const float4 *B, con
 // idx: as many words as idxO.  tmp (n words) and o2s (n words) are scratch.
 cudaError_t remapNeighbors(const uint32_t *s2o, const uint32_t *offO, const uint32_t *idxO,
                            uint32_t n, uint32_t *o2s, uint32_t *cnt, uint32_t *off, uint32_t *idx,
-                           cudaStream_t s) {
+                           uint32_t *row, cudaStream_t s) {
   invertAndCountKernel<<<(n + 255) / 256, 256, 0, s>>>(s2o, offO, n, o2s, cnt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
@@ -505,8 +523,7 @@ cudaError_t remapNeighbors(const uint32_t *s2o, const uint32_t *offO, const uint
   if (e != cudaSuccess)
     return e;
   closeOffsetsKernel<<<1, 1, 0, s>>>(cnt, n, off);
-  if (offO && idxO)
-    remapRowsKernel<<<(n + 255) / 256, 256, 0, s>>>(s2o, o2s, offO, idxO, off, n, idx);
+  remapRowsKernel<<<(n + 255) / 256, 256, 0, s>>>(s2o, o2s, offO, idxO, off, n, idx, row);
   return cudaGetLastError();
 }
 

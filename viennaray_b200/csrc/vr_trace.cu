@@ -22,6 +22,7 @@
 // to running each ray to completion on its own (per-ray counter RNG, fixed
 // point flux sums), which is what the CPU oracle does.
 #include "vr_device.cuh"
+#include <cstdlib>
 
 namespace vr {
 
@@ -74,7 +75,7 @@ __device__ __forceinline__ bool slotEmpty(const float4 &od0) { return od0.w != o
 // places, and eight inlined triangle tests per call site pushed that kernel to
 // 123 KB of SASS (instruction-fetch stalls were 23 % of its samples).
 // (arguments and result by value: a real call that keeps everything in registers)
-__device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, const V3 dir) {
+__device__ __noinline__ Hit boundaryTestGeneric(const DeviceScene &sc, const V3 org, const V3 dir) {
   Hit best;
   best.t = 3.402823466e+38f;
   best.geom = best.prim = best.orig = VR_INVALID_ID;
@@ -139,6 +140,79 @@ __device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, co
       testTri(v0, v1, v2, 0u, (uint32_t)i, (uint32_t)i, org, dir, best, nullptr);
     }
   }
+  return best;
+}
+
+// The same closest hit with a shortcut for the usual case (lateral axes x and y, sc.bFast).
+// A ray that starts inside the box leaves it through one of the two planes it moves
+// towards.  When plain plane distances show that (a) neither plane behind the ray is a
+// candidate, (b) the nearer exit plane is crossed clearly inside one of its two triangles
+// -- or clearly above / below the box, a miss -- the triangle is known and only its t is
+// computed, with the very float operations of testTri: for an axis-aligned triangle
+// Ng = cross(e2, e1) has one non-zero component N (sc.bN), the other products of
+// dot(Ng, C) and dot(Ng, dir) are exact zeros, and t = fl(fl(N C_a) / fl(N d_a)) (a
+// division is symmetric in the signs, so the den < 0 branch of testTri gives the same
+// bits).  A miss is declared with exactly the candidate rule of boundaryTestGeneric (same
+// expressions, same margin m), a hit with four times that margin; a ray inside a margin (corners, edges, the diagonal, a start on or
+// behind a plane) takes boundaryTestGeneric.  Same results, about a fifth of the
+// instructions (the boundary tests were 38 % of the shade kernel's).
+__device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, const V3 dir) {
+  if (!sc.bFast)
+    return boundaryTestGeneric(sc, org, dir);
+  const float INF = __int_as_float(0x7f800000);
+  const bool px = dir.x > 0.f, py = dir.y > 0.f;
+  const float lox = sc.bbox[0][0], hix = sc.bbox[1][0], loy = sc.bbox[0][1], hiy = sc.bbox[1][1];
+  const float loz = sc.bbox[0][2], hiz = sc.bbox[1][2];
+  const float rdx = __fdividef(1.f, dir.x), rdy = __fdividef(1.f, dir.y);
+  // distance to the plane ahead (exit) and to the plane behind (entry) per lateral axis
+  float txe = ((px ? hix : lox) - org.x) * rdx, txn = ((px ? lox : hix) - org.x) * rdx;
+  float tye = ((py ? hiy : loy) - org.y) * rdy, tyn = ((py ? loy : hiy) - org.y) * rdy;
+  if (dir.x == 0.f) {
+    txe = INF;
+    txn = -INF;
+  }
+  if (dir.y == 0.f) {
+    tye = INF;
+    tyn = -INF;
+  }
+  const bool xFirst = txe < tye;
+  const float t0 = xFirst ? txe : tye;
+  // (NaN from 0 * inf fails the comparisons and takes the generic path)
+  bool clear = txn < 0.25f * VR_TNEAR && tyn < 0.25f * VR_TNEAR && t0 >= 2.f * VR_TNEAR &&
+               org.z >= loz && org.z <= hiz;
+  Hit best;
+  best.t = 3.402823466e+38f;
+  best.geom = best.prim = best.orig = VR_INVALID_ID;
+  if (clear && t0 == INF)
+    return best;  // parallel to all four planes
+  const float m = 1e-4f * (sc.bExt + t0);
+  const float hu = org.z + dir.z * t0;
+  if (clear && (hu < loz - m || hu > hiz + m))
+    return best;  // leaves through the top or the bottom: every later plane point is farther out
+  // the crossing point on the plane: f along the other lateral axis, u along z
+  const float hf = xFirst ? org.y + dir.y * t0 : org.x + dir.x * t0;
+  const float lof = xFirst ? loy : lox, hif = xFirst ? hiy : hix;
+  // (the triangle test decides inside / outside to within ~1e-7 |C| / |d_a| of an edge: with
+  // |d_a| >= 0.01 that is a tenth of the margin 4 m)
+  const float mi = 4.f * m;
+  clear = clear && hf > lof + mi && hf < hif - mi && hu > loz + mi && hu < hiz - mi &&
+          fabsf(xFirst ? dir.x : dir.y) >= 0.01f;
+  // side of the diagonal (lof, loz) - (hif, hiz)
+  const float Lf = hif - lof, Lz = hiz - loz;
+  const float a = (hf - lof) * Lz, b = (hu - loz) * Lf;
+  clear = clear && fabsf(a - b) > 1e-3f * (Lf * Lz);
+  if (!clear)
+    return boundaryTestGeneric(sc, org, dir);
+  // x planes: triangles 0, 1 (low), 2, 3 (high), the lower index below the diagonal;
+  // y planes: 4, 5 (low), 6, 7 (high), the lower index above it (vr_scene_set_boundary)
+  const bool upper = b > a;
+  const int i = xFirst ? (px ? 2 : 0) + (upper ? 1 : 0) : (py ? 6 : 4) + (upper ? 0 : 1);
+  const float N = sc.bN[i];
+  const float T = N * (sc.bX[i] - (xFirst ? org.x : org.y));
+  const float den = N * (xFirst ? dir.x : dir.y);
+  best.t = T / den;
+  best.geom = 0u;
+  best.prim = best.orig = (uint32_t)i;
   return best;
 }
 
@@ -246,6 +320,39 @@ __device__ __forceinline__ void slabChild(const uint4 c, const NodeRay &r, float
   const float fz = __fmaf_rn(__uint_as_float(__byte_perm(c.z, M, qz)), r.iz, r.oz);
   n = fmaxf(fmaxf(nx, ny), fmaxf(nz, VR_TNEAR));
   f = fminf(fminf(fx, fy), fminf(fz, tmax));
+}
+
+// prefetch variants of the traverse kernel (off unless built with -DVR_PF_*=1)
+#ifndef VR_PF_KIDS
+#define VR_PF_KIDS 0  // both children of a node as soon as the node has arrived
+#endif
+#ifndef VR_PF_PUSH
+#define VR_PF_PUSH 0  // the deferred child at the time it is pushed
+#endif
+#ifndef VR_PF_LEAF
+#define VR_PF_LEAF 0  // a leaf's disks when a lane leaves the node loop: 1 first, 2 first + last, 4 all
+#endif
+#ifndef VR_PF_POP
+#define VR_PF_POP 0  // the popped entry before the leaf's tests run
+#endif
+template <int GEO>
+__device__ __forceinline__ void prefetchLeaf(const DeviceScene &sc, uint32_t ref) {
+  const uint32_t first = (ref & 0x7fffffffu) >> 4;
+  constexpr int stride = GEO ? 4 : 2;
+  prefetchL1(&sc.prim[(size_t)stride * first]);
+#if VR_PF_LEAF == 2
+  prefetchL1(&sc.prim[(size_t)stride * (first + (ref & 15u)) - 1]);
+#elif VR_PF_LEAF == 4
+  for (uint32_t k = 1; k < (ref & 15u); ++k)
+    prefetchL1(&sc.prim[(size_t)stride * (first + k)]);
+#endif
+}
+template <int GEO>
+__device__ __forceinline__ void prefetchRef(const DeviceScene &sc, uint32_t ref) {
+  if (ref < VR_DONE)
+    prefetchL1(sc.nodes + ref);
+  else
+    prefetchLeaf<GEO>(sc, ref);
 }
 
 // ---------------------------------------------------------------------------
@@ -503,8 +610,15 @@ __global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
           c0 = q[0];
           c1 = q[1];
         } else {
-          ldg256(sc.nodes + cur, c0, c1);
+          ldgNode(sc.nodes + cur, c0, c1);
         }
+#if VR_PF_KIDS
+        // both children's records requested while this node's boxes are tested
+        if (c0.w < VR_DONE)
+          prefetchL1(sc.nodes + c0.w);
+        if (c1.w < VR_DONE)
+          prefetchL1(sc.nodes + c1.w);
+#endif
         if (COUNT)
           ++wNodes;
         // slab tests with an explicit FMA per plane (slabChild); the boxes were
@@ -517,8 +631,12 @@ __global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
         const bool h1 = n1 <= __fmaf_rn(f1, 1.00003f, 2e-6f);
         const uint32_t r0 = c0.w, r1 = c1.w;
         const bool swap = n1 < n0;
-        if (h0 && h1)
+        if (h0 && h1) {
           VR_PUSH(swap ? r0 : r1)
+#if VR_PF_PUSH
+          prefetchRef<GEO>(sc, swap ? r0 : r1);  // in L1 by the time it is popped
+#endif
+        }
         if (h0 || h1) {
           cur = (h0 && (!h1 || !swap)) ? r0 : r1;
         } else {
@@ -526,6 +644,11 @@ __global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
           if (sp)
             VR_POP(cur)
         }
+#if VR_PF_LEAF
+        // a lane that reached a leaf waits for the others: its disks travel meanwhile
+        if (cur > VR_DONE)
+          prefetchLeaf<GEO>(sc, cur);
+#endif
       }
     }
 
@@ -535,11 +658,15 @@ __global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
       cur = VR_DONE;
       if (sp)
         VR_POP(cur)
+#if VR_PF_POP
+      if (cur != VR_DONE)
+        prefetchRef<GEO>(sc, cur);  // the next node / leaf travels during this leaf's tests
+#endif
       for (uint32_t k = 0; k < count; ++k) {
         const uint32_t i = first + k;
         if (GEO == 0) {
           float4 P, N;
-          ldg256(&sc.prim[2 * i], P, N);
+          ldgDisk(&sc.prim[2 * i], P, N);
           testDisk(P, N, i, org, dir, best);
         } else {
           const float4 a = __ldg(&sc.prim[4 * i]), b = __ldg(&sc.prim[4 * i + 1]),
@@ -596,6 +723,15 @@ static cudaError_t launchTraverseT(const TraceParams &p, int numSMs, cudaStream_
   }
   unsigned want = (p.numSlots + (unsigned)T - 1u) / (unsigned)T;
   unsigned grid = (unsigned)(numSMs * perSM);
+  {  // experiment knob: resident traverse blocks per SM (co-residency with another kernel)
+    static int cap = -1;
+    if (cap < 0) {
+      const char *e = getenv("VR_TRAV_CAP");
+      cap = e ? atoi(e) : 0;
+    }
+    if (cap > 0 && cap < perSM)
+      grid = (unsigned)(numSMs * cap);
+  }
   if (want < grid)
     grid = want;
   traverseKernel<GEO, WIDE, COUNT, TOP><<<grid, T, smem, s>>>(p);
@@ -778,6 +914,79 @@ struct Tally {
   unsigned cTraces, cMiss, cGeo, cBnd, cRefl, cTerm, wNb, wFlux, wSky, cScatter;
 };
 
+// Neighbour spread of one geometry hit (rayTraceKernel.hpp:271-280): every neighbour of the
+// hit disk that the ray also intersects (checkLocalIntersection) receives the weight.  The
+// lists are read from 8-wide rows (sc.nbRow: the first eight neighbours of a disk in one
+// 256-bit load, bit 31 of the eighth word = "the CSR holds more"), so the common disk --
+// eight neighbours on a flat grid -- needs no offset lookup and no scalar index loads; four
+// disks are requested per round so the gathers overlap.  Integer sums: order-free.
+#ifndef VR_NB_ROWS
+#define VR_NB_ROWS 1  // 0: the CSR only (A/B switch)
+#endif
+__device__ __forceinline__ void spreadNeighbors(const TraceParams &p, const uint32_t hprim,
+                                                const V3 &org, const V3 &dir,
+                                                const unsigned long long wf, unsigned &wNb,
+                                                unsigned &wFlux) {
+  const DeviceScene &sc = p.scene;
+  uint32_t id[4];
+  uint32_t k = 0u, k1 = 0u;
+#if VR_NB_ROWS
+  uint4 ra, rb;
+  ldg256(sc.nbRow + 2 * (size_t)hprim, ra, rb);
+  const bool more = rb.w != VR_INVALID_ID && (rb.w >> 31) != 0u;
+  if (more)
+    rb.w &= 0x7fffffffu;
+  id[0] = ra.x, id[1] = ra.y, id[2] = ra.z, id[3] = ra.w;
+  int round = 0;
+#else
+  k = __ldg(&sc.nbOff[hprim]);
+  k1 = __ldg(&sc.nbOff[hprim + 1]);
+#endif
+  // one copy of the round's code for the two halves of the row and the rare CSR rounds
+  for (;;) {
+#if !VR_NB_ROWS
+    if (k >= k1)
+      break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
+    k += 4u;
+#endif
+    float4 P[4], Nn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (id[j] != VR_INVALID_ID)
+        ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (id[j] != VR_INVALID_ID) {
+        ++wNb;
+        if (checkLocal(P[j], Nn[j], org, dir)) {
+          atomicAdd(&p.flux[id[j]], wf);
+          ++wFlux;
+        }
+      }
+#if VR_NB_ROWS
+    if (++round == 1) {
+      id[0] = rb.x, id[1] = rb.y, id[2] = rb.z, id[3] = rb.w;
+      continue;
+    }
+    if (!more)
+      break;
+    if (round == 2) {
+      k = __ldg(&sc.nbOff[hprim]) + 8u;
+      k1 = __ldg(&sc.nbOff[hprim + 1]);
+    }
+    if (k >= k1)
+      break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
+    k += 4u;
+#endif
+  }
+}
+
 // What rayTraceKernel.hpp:169-333 does with the hit (t, prim, geom) of a ray: miss,
 // boundary handling, back-face rule, neighbour spread, particle functor, roulette, and
 // the sky map's shortcut for rays that leave the scene.  Returns true when the ray ended.
@@ -896,31 +1105,8 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, cons
         const unsigned long long wf = toFixed(w);
         atomicAdd(&p.flux[hprim], wf);  // :297-306 surfaceCollision
         ++wFlux;
-        if (GEO == 0) {  // :271-280 neighbour spread
-          const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
-          // four neighbours per round: all index loads, then all disk loads,
-          // then the tests, so the gathers overlap
-          for (uint32_t k = k0; k < k1; k += 4) {
-            uint32_t id[4];
-            float4 P[4], Nn[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (id[j] != VR_INVALID_ID)
-                ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (id[j] != VR_INVALID_ID) {
-                ++wNb;
-                if (checkLocal(P[j], Nn[j], org, dir)) {
-                  atomicAdd(&p.flux[id[j]], wf);
-                  ++wFlux;
-                }
-              }
-          }
-        }
+        if (GEO == 0)  // :271-280 neighbour spread
+          spreadNeighbors(p, hprim, org, dir, wf, wNb, wFlux);
       }
       if (!rngLoaded) {
         rng.load(rs, p.seed, p.stream, idx);
@@ -1152,27 +1338,7 @@ __global__ void __launch_bounds__(256) spreadKernel(const __grid_constant__ Trac
     const unsigned long long wf = toFixed(a.w);
     atomicAdd(&p.flux[hprim], wf);
     ++wFlux;
-    const uint32_t k0 = __ldg(&sc.nbOff[hprim]), k1 = __ldg(&sc.nbOff[hprim + 1]);
-    for (uint32_t k = k0; k < k1; k += 4) {
-      uint32_t id[4];
-      float4 P[4], Nn[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        id[j] = (k + j < k1) ? __ldg(&sc.nbIdx[k + j]) : VR_INVALID_ID;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (id[j] != VR_INVALID_ID)
-          ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (id[j] != VR_INVALID_ID) {
-          ++wNb;
-          if (checkLocal(P[j], Nn[j], org, dir)) {
-            atomicAdd(&p.flux[id[j]], wf);
-            ++wFlux;
-          }
-        }
-    }
+    spreadNeighbors(p, hprim, org, dir, wf, wNb, wFlux);
   }
   if (p.work) {
     const unsigned a = __reduce_add_sync(0xffffffffu, wNb), b = __reduce_add_sync(0xffffffffu, wFlux);
@@ -1320,13 +1486,22 @@ cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int com
 }
 
 template <int EXT> static void launchShadeExt(const TraceParams &p, unsigned grid, cudaStream_t s) {
+  // experiment knob: dynamic shared memory padding that limits the shade kernel's resident
+  // blocks per SM (co-residency with the traverse kernel of another stream)
+  static int pad = -1;
+  if (pad < 0) {
+    const char *e = getenv("VR_SHADE_SMEM_PAD");
+    pad = e ? atoi(e) : 0;
+    if (pad > 0)
+      cudaFuncSetAttribute(shadeKernel<3, 0, EXT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+  }
   if (p.scene.geoType == 0) {
     if (p.scene.D == 2)
       shadeKernel<2, 0, EXT, 0><<<grid, 256, 0, s>>>(p);
     else if (!EXT && p.spreadQ)  // neighbour spread queued for spreadKernel
       shadeKernel<3, 0, 0, 1><<<grid, 256, 0, s>>>(p);
     else
-      shadeKernel<3, 0, EXT, 0><<<grid, 256, 0, s>>>(p);
+      shadeKernel<3, 0, EXT, 0><<<grid, 256, pad, s>>>(p);
   } else {
     if (p.scene.D == 2)
       shadeKernel<2, 1, EXT, 0><<<grid, 256, 0, s>>>(p);
