@@ -314,8 +314,9 @@ def main():
     per_ray = {k: v / float(npart * count_rays) for k, v in work.items()}
     trav_bytes_per_ray = per_ray["node_visits"] * node_b + per_ray["prim_tests"] * prim_b
     bytes_per_ray = trav_bytes_per_ray + per_ray["nb_tests"] * (4 + 32) + per_ray["flux_adds"] * 8
-    nb_entries = 8.0 * n  # ~8 neighbours per disk (exact count is on the device)
-    scene_bytes = n * 32 + bvh["nodes"] * node_b + nb_entries * 4 + (n + 1) * 4
+    # what the kernels fetch from: disk records, nodes, 8-wide neighbour rows (the CSR behind
+    # the rows is read for the few disks with more than eight neighbours only)
+    scene_bytes = n * 32 + bvh["nodes"] * node_b + n * 32
 
     # warm-up
     for k in range(args.warmup):
@@ -430,6 +431,19 @@ def main():
                 "times with 16-byte ld.global.cg loads") if l2_resident else hbm_src
     traffic = traffic_capture(args.config)
     step_gbps = value / world * bytes_per_ray / 1e9
+    clocks = sampler.summary()
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    lsu_peak = sms * (clocks["sm_mhz"] or 1965.0) * 1e6
+    fetches = (per_ray["node_visits"] + per_ray["prim_tests"]) * float(npart) * my_rays * args.steps
+    lsu = {"unit": "L1 data-stage wavefronts/s", "peak": lsu_peak,
+           "peak_source": "%d SMs x %.0f MHz (sampled under load), one wavefront per cycle per SM"
+                          % (sms, clocks["sm_mhz"] or 1965.0),
+           "achieved": fetches / (trav_ms * 1e-3), "frac": fetches / (trav_ms * 1e-3) / lsu_peak}
+    if traffic and traffic.get("traverse_lsu_wavefronts_per_traversal"):
+        w = traffic["traverse_lsu_wavefronts_per_traversal"]
+        rate = traversals_per_launch * trav_launches / (trav_ms * 1e-3)
+        lsu["measured_wavefronts_per_traversal"] = w
+        lsu["measured_frac"] = w * rate / lsu_peak
     line = {
         "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -448,6 +462,10 @@ def main():
                         "reused, one BVH build); `cold_value`: the first step of a fresh context "
                         "(pool allocation, three BVH builds)"},
         "gpu_launches": launches,
+        "lanes": ("the particles of a trace (or the two halves of a lone particle's ray range) run "
+                  "two at a time on two streams (VR_LANES=2); the per-kernel durations under "
+                  "`roofline` come from a second pass over the same steps with one lane and CUDA "
+                  "events around every launch"),
         "roofline": {
             "kernel": "traverseKernel<0,0,0,0>", "bound": bound, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak if peak else None,
@@ -455,6 +473,12 @@ def main():
             "hbm": {"peak": hbm_peak, "peak_source": hbm_src, "frac": achieved / hbm_peak},
             "l2": {"size_bytes": l2_bytes, "read_gbps": l2_gbps,
                    "frac_of_l2_read": achieved / l2_gbps if l2_gbps else None},
+            # The unit that saturates first: every lane's 32-byte node / disk
+            # fetch is one wavefront of the L1 data stage, which passes one per cycle per SM.
+            # achieved: counted node visits + primitive tests per second of traverse-kernel
+            # time; measured: ncu l1tex__data_pipe_lsu_wavefronts of the captured launch per
+            # traversal (pool and stack accesses included) x this run's traversal rate
+            "lsu": lsu,
             "scene_bytes": scene_bytes,
             # DRAM bytes of an average launch: ncu's dram__bytes_{read,write}.sum per traversed
             # slot of one captured launch (profiles/r*_traffic.json) x traversals per launch
@@ -479,7 +503,7 @@ def main():
                     "`peak`: the memory level the scene is served from -- L2 when it fits the L2 "
                     "cache (measured read bandwidth of this run), HBM otherwise "
                     "(MEASURED_PEAKS.json); `hbm.frac` is the same rate over the HBM peak" % node_b},
-        "clocks": sampler.summary(),
+        "clocks": clocks,
         "bvh": bvh, "first_commit_s": t_first_commit,
         "walk": {"traces_per_ray": [i.totalRaysTraced / count_rays for i in cinfo],
                  "geo_hits_per_ray": [i.geometryHits / count_rays for i in cinfo]},

@@ -205,3 +205,34 @@ def test_spread_kernel_option(monkeypatch, name, tail):
     monkeypatch.setenv("VR_POOL_SLOTS", "16384")
     c = common.case(name)
     run_pair(c, 150000)
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 3, 4])
+@pytest.mark.parametrize("pool", [8192, 0])
+def test_wavefront_lanes_do_not_change_results(monkeypatch, lanes, pool):
+    """VR_LANES: the jobs of a trace -- one per particle, or the pieces of a particle's ray range
+    when there are fewer particles than lanes -- run side by side on their own streams, pools
+    and host threads (vr_api.cu, vr_ctx::xlane).  Three particles in one call: flux words and
+    counters of every particle must be the oracle's for any number of lanes."""
+    monkeypatch.setenv("VR_LANES", str(lanes))
+    if pool:
+        monkeypatch.setenv("VR_POOL_SLOTS", str(pool))
+    c = common.case("trench")
+    orc = common.make_oracle(c)
+    ctx, src, _ = common.make_gpu(c)
+    num = 200000
+    descs = [PARTICLES["diffuse"], PARTICLES["coned"], PARTICLES["specular"]]
+    ctx.trace_device(src, [capi.ParticleDesc(*d) for d in descs], host.config(num, SEED), sync=True)
+    fg = ctx.flux_download_fixed()
+    ig = ctx.flux_download()[1]
+    for k, d in enumerate(descs):
+        fo, io = orc.trace(po.Particle(*d), orc.config(num, SEED, stream=k))
+        assert (fg[k] == fo).all(), "particle %d: %d primitives differ" % (k, int((fg[k] != fo).sum()))
+        assert (ig[k].totalRaysTraced, ig[k].geometryHits, ig[k].boundaryHits, ig[k].reflections) == \
+            (io.totalTraces, io.geoHits, io.boundaryHits, io.reflections)
+    # a lone particle: its range is cut into pieces when it is long enough for the pool
+    ctx.trace_device(src, [capi.ParticleDesc(*descs[0])], host.config(num, SEED), sync=True)
+    fo, io = orc.trace(po.Particle(*descs[0]), orc.config(num, SEED))
+    assert (ctx.flux_download_fixed()[0] == fo).all()
+    assert ctx.flux_download()[1][0].totalRaysTraced == io.totalTraces
+    ctx.close()

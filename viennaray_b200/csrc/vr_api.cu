@@ -1344,7 +1344,7 @@ int vr_trace_device(vr_ctx *ctx, const vr_source_desc *src, const vr_particle_de
   const uint32_t slots = (uint32_t)std::min<uint64_t>(ctx->poolSlots, std::max<uint64_t>(shardRays, 1));
   CK(ensurePool(ctx, slots));
   // neighbour spread in its own kernel?
-  const size_t sceneBytes = (size_t)n * 32 + ctx->nbTotal * 4 + ((size_t)n + 1) * 4;
+  const size_t sceneBytes = (size_t)n * 32 + (size_t)n * 32;  // disk records + neighbour rows
   const bool spreadSplit = ctx->geoType == 0 && ctx->D == 3 &&
                            (ctx->spreadMode == 1 || (ctx->spreadMode < 0 && sceneBytes > ctx->l2Bytes));
   if (spreadSplit && ctx->spreadCap < slots) {
