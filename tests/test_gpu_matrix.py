@@ -236,3 +236,13 @@ def test_wavefront_lanes_do_not_change_results(monkeypatch, lanes, pool):
     assert (ctx.flux_download_fixed()[0] == fo).all()
     assert ctx.flux_download()[1][0].totalRaysTraced == io.totalTraces
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["trench", "trench_ion", "holes", "disk3D"])
+def test_boundary_test_without_its_shortcut(monkeypatch, name):
+    """VR_BOUNDARY_GENERIC: every boundary hit through the candidate planes and the exact
+    triangle tests (the path the shortcut of boundaryTest, vr_trace.cu, falls back to inside
+    its margins).  Every other test runs with the shortcut; both must give the oracle's flux
+    words and counters (periodic and reflective boundaries, sky-map walks)."""
+    monkeypatch.setenv("VR_BOUNDARY_GENERIC", "1")
+    run_pair(common.case(name), 150000)
