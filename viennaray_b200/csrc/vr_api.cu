@@ -247,10 +247,12 @@ static void freeResults(vr_ctx *c) {
 }
 
 static void freeOnePool(RayPool &q) {
-  cudaFree(q.ray);
+  cudaFree(q.od0);
+  cudaFree(q.od1);
   cudaFree(q.hit);
+  cudaFree(q.rng);
   cudaFree(q.meta);
-  cudaFree(q.wr);
+  cudaFree(q.weight);
   cudaFree(q.dir3);
   q = RayPool{};
 }
@@ -270,10 +272,12 @@ static void freePool(vr_ctx *c) {
 }
 static cudaError_t allocOnePool(RayPool &q, uint32_t slots) {
   cudaError_t e;
-  if ((e = cudaMalloc(&q.ray, sizeof(float4) * 2 * (size_t)slots)) != cudaSuccess ||
-      (e = cudaMalloc(&q.hit, sizeof(float2) * (size_t)slots)) != cudaSuccess ||
+  if ((e = cudaMalloc(&q.od0, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.od1, sizeof(float2) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.hit, sizeof(float4) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.rng, sizeof(uint32_t) * (size_t)slots)) != cudaSuccess ||
       (e = cudaMalloc(&q.meta, sizeof(uint4) * (size_t)slots)) != cudaSuccess ||
-      (e = cudaMalloc(&q.wr, sizeof(float2) * (size_t)slots)) != cudaSuccess ||
+      (e = cudaMalloc(&q.weight, sizeof(float) * (size_t)slots)) != cudaSuccess ||
       (e = cudaMalloc(&q.dir3, sizeof(float4) * (size_t)slots)) != cudaSuccess)
     return e;
   q.capacity = slots;
@@ -281,7 +285,7 @@ static cudaError_t allocOnePool(RayPool &q, uint32_t slots) {
 }
 // two pools: the tail of a trace compacts survivors from one into the other
 static cudaError_t ensurePool(vr_ctx *c, uint32_t slots) {
-  if (c->pool.capacity >= slots && c->pool.ray && c->pool2.ray)
+  if (c->pool.capacity >= slots && c->pool.od0 && c->pool2.od0)
     return cudaSuccess;
   freePool(c);
   cudaError_t e = allocOnePool(c->pool, slots);
@@ -306,7 +310,7 @@ static cudaError_t ensureLane(vr_ctx *c, int which, uint32_t slots, bool spreadS
         (e = cudaMallocHost(&l.hLive, 8 * sizeof(unsigned int))) != cudaSuccess)
       return e;
   }
-  if (!(l.pool.capacity >= slots && l.pool.ray && l.pool2.ray)) {
+  if (!(l.pool.capacity >= slots && l.pool.od0 && l.pool2.od0)) {
     freeOnePool(l.pool);
     freeOnePool(l.pool2);
     if ((e = allocOnePool(l.pool, slots)) != cudaSuccess ||

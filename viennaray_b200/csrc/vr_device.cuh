@@ -51,20 +51,6 @@ __device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
                  "=r"(b.w)
                : "l"(p));
 }
-// streaming (evict-first) 256-bit access to a ray-pool record: the pool passes through the
-// L2 once per kernel and must not push the scene out of it
-__device__ __forceinline__ void ldcs256(const float4 *p, float4 &a, float4 &b) {
-  asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z),
-                 "=f"(b.w)
-               : "l"(p));
-}
-__device__ __forceinline__ void stcs256(float4 *p, const float4 a, const float4 b) {
-  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x),
-               "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
-               : "memory");
-}
-
 // tuning variants of the traverse kernel's loads (measured in DESIGN.md section 4): cache
 // policy of the node / disk records in L1 and prefetches into L1
 #ifndef VR_NODE_LD
@@ -298,16 +284,6 @@ struct Hit {
   uint32_t prim;  // internal index for geometry, 0..7 for the boundary
   uint32_t orig;  // original primitive ID (tie-break key)
 };
-// hit word of the ray pool (vr_internal.h, RayPool)
-__device__ __forceinline__ uint32_t hitWord(uint32_t geom, uint32_t prim) {
-  return geom == VR_INVALID_ID ? VR_INVALID_ID : (geom ? (0x80000000u | prim) : prim);
-}
-__device__ __forceinline__ uint32_t hitWordGeom(uint32_t word) {
-  return word == VR_INVALID_ID ? VR_INVALID_ID : (word >> 31);
-}
-__device__ __forceinline__ uint32_t hitWordPrim(uint32_t word) {
-  return word == VR_INVALID_ID ? VR_INVALID_ID : (word & 0x7fffffffu);
-}
 // smallest t, then lower geomID, then lower original primID; written without branches
 // (t and b.t are never NaN here) because only a few lanes of a warp ever get this far
 __device__ __forceinline__ bool better(float t, uint32_t geom, uint32_t orig, const Hit &b) {

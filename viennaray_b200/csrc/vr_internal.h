@@ -82,21 +82,18 @@ struct DeviceScene {
   float bN[8], bX[8];
 };
 
-// Resident pool of rays in flight, one slot per ray.
-//   ray   32 bytes, one 256-bit load or store: {org.xyz, dir.x}, {dir.y, dir.z, t of the ray's
-//         boundary hit, hit word of the boundary hit}.  Written by the shade / init kernel
-//         (which intersects the boundary box), read by the traverse kernel as the traversal's
-//         initial best.  A slot with dir.x = NaN is empty.
-//   hit   the traverse kernel's result {t, hit word}
-//   meta, wr, dir3   owned by the shade kernel
-// Hit word: VR_INVALID_ID = miss, bit 31 set = geometry (internal primitive index in the low
-// bits), else the boundary triangle 0..7.
+// Resident pool of rays in flight (structure of arrays, one slot per ray).
+// The traverse kernel reads od0/od1, starts from hit (the ray's boundary hit, found by the
+// shade / init kernel) and writes the closest hit back; the shade kernel owns the rest.
+// A slot with dir.x = NaN is empty.
 struct RayPool {
   uint32_t capacity;
-  float4 *ray;   // 2 per slot
-  float2 *hit;   // t, hit word (bits)
+  float4 *od0;   // org.x, org.y, org.z, dir.x
+  float2 *od1;   // dir.y, dir.z
+  float4 *hit;   // t, prim (bits), geom (bits), -
+  uint32_t *rng; // next block of the ray's Philox stream (vr_device.cuh, struct Rng)
   uint4 *meta;   // idx lo, idx hi, numReflections, boundaryHits | hitFromBack << 31
-  float2 *wr;    // weight, next block of the ray's Philox stream (bits; vr_device.cuh, Rng)
+  float *weight;
   float4 *dir3;  // particle-facing direction (differs from the ray's in 2D only)
 };
 

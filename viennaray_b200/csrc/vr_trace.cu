@@ -216,11 +216,12 @@ __device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, co
   return best;
 }
 
-// a ray and its boundary hit (the traversal's initial best) as one 32-byte pool record
-__device__ __forceinline__ void storeRayRecord(const RayPool &pool, uint32_t s, const V3 &org,
-                                               const V3 &dir, const Hit &bh) {
-  stcs256(pool.ray + 2 * (size_t)s, make_float4(org.x, org.y, org.z, dir.x),
-          make_float4(dir.y, dir.z, bh.t, __uint_as_float(hitWord(bh.geom, bh.prim))));
+// closest boundary hit of a fresh ray, stored as the traversal's initial best
+__device__ __forceinline__ void storeBoundaryHit(const DeviceScene &sc, const RayPool &pool,
+                                                 uint32_t s, const V3 &org, const V3 &dir) {
+  const Hit best = boundaryTest(sc, org, dir);
+  __stcs(&pool.hit[s],
+         make_float4(best.t, __uint_as_float(best.prim), __uint_as_float(best.geom), 0.f));
 }
 
 // Sky test: may the ray leaving `org` towards the source be declared free of
@@ -514,17 +515,18 @@ __global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
       if (slot == VR_INVALID_ID) {
         const unsigned s = base + __popc(need & ltMask);
         if (s < numSlots) {
-          float4 a, b;  // the ray and its boundary hit: one 256-bit load
-          ldcs256(p.pool.ray + 2 * (size_t)s, a, b);
+          const float4 a = __ldcs(&p.pool.od0[s]);
           if (!slotEmpty(a)) {
+            const float2 b = __ldcs(&p.pool.od1[s]);
             slot = s;
             org = {a.x, a.y, a.z};
             dir = {a.w, b.x, b.y};
             nr = makeNodeRay(sc, org, dir);
             // the shade / init kernel already intersected the boundary box
-            best.t = b.z;
-            best.prim = best.orig = hitWordPrim(__float_as_uint(b.w));
-            best.geom = hitWordGeom(__float_as_uint(b.w));
+            const float4 h0 = __ldcs(&p.pool.hit[s]);
+            best.t = h0.x;
+            best.prim = best.orig = __float_as_uint(h0.y);
+            best.geom = __float_as_uint(h0.z);
             sp = 0;
             cur = sc.numPrims ? (TOP ? VR_TOP_BASE : sc.rootRef) : VR_DONE;
           }
@@ -679,8 +681,8 @@ __global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
 
     // ---- finished: publish the hit, free the lane ---------------------------------
     if (slot != VR_INVALID_ID && cur == VR_DONE) {
-      __stcs(&p.pool.hit[slot],
-             make_float2(best.t, __uint_as_float(hitWord(best.geom, best.prim))));
+      __stcs(&p.pool.hit[slot], make_float4(best.t, __uint_as_float(best.prim),
+                                            __uint_as_float(best.geom), 0.f));
       slot = VR_INVALID_ID;
     }
   }
@@ -843,22 +845,20 @@ __device__ __forceinline__ bool regenerate(const TraceParams &p, bool want, uint
   return true;
 }
 
-// a slot's whole state: the ray record (with the ray's boundary hit bh) and the walk's state
 template <int D>
 __device__ __forceinline__ void storeRay(const RayPool &pool, uint32_t s, const V3 &org,
                                          const V3 &dir, const V3 &rayDirection, float w,
-                                         uint32_t rngBlock, uint64_t idx, uint32_t numReflections,
-                                         uint32_t boundaryHits, bool hitFromBack, const Hit &bh) {
+                                         const Rng &rng, uint64_t idx, uint32_t numReflections,
+                                         uint32_t boundaryHits, bool hitFromBack) {
   // the pool is streamed (evict-first) so that the scene keeps the L2
-  storeRayRecord(pool, s, org, dir, bh);
+  __stcs(&pool.od0[s], make_float4(org.x, org.y, org.z, dir.x));
+  __stcs(&pool.od1[s], make_float2(dir.y, dir.z));
+  __stcs(&pool.rng[s], rng.save());
   __stcs(&pool.meta[s], make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
                                    boundaryHits | (hitFromBack ? 0x80000000u : 0u)));
-  __stcs(&pool.wr[s], make_float2(w, __uint_as_float(rngBlock)));
+  __stcs(&pool.weight[s], w);
   if (D == 2)
     __stcs(&pool.dir3[s], make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f));
-}
-__device__ __forceinline__ void storeEmptySlot(const RayPool &pool, uint32_t s) {
-  pool.ray[2 * (size_t)s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
 }
 
 // ---------------------------------------------------------------------------
@@ -874,11 +874,12 @@ template <int D> __global__ void __launch_bounds__(256) initPoolKernel(const Tra
   const bool ok = regenerate<D>(p, inRange, idx, rng, org, rd, dir);
   if (!inRange)
     return;
-  if (ok)
-    storeRay<D>(p.pool, s, org, dir, rd, 1.f, rng.save(), idx, 0u, 0u, false,
-                boundaryTest(p.scene, org, dir));
-  else
-    storeEmptySlot(p.pool, s);
+  if (ok) {
+    storeRay<D>(p.pool, s, org, dir, rd, 1.f, rng, idx, 0u, 0u, false);
+    storeBoundaryHit(p.scene, p.pool, s, org, dir);
+  } else {
+    p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
+  }
 }
 
 cudaError_t launchInitPool(const TraceParams &p, cudaStream_t s) {
@@ -1190,9 +1191,8 @@ __global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) 
   Tally c = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   bool live = false, finish = false;
   float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
-  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s < numSlots)
-    ldcs256(p.pool.ray + 2 * (size_t)s, a, a1);  // the ray (its boundary hit is not needed here)
+    a = __ldcs(&p.pool.od0[s]);
   live = !slotEmpty(a);
 
   RayState r;
@@ -1217,44 +1217,54 @@ __global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) 
   uint32_t &rs = r.rs;
 
   if (live) {
-    dir = {a.w, a1.x, a1.y};
+    const float2 b = __ldcs(&p.pool.od1[s]);
+    dir = {a.w, b.x, b.y};
     if (D == 2) {
       const float4 d3 = __ldcs(&p.pool.dir3[s]);
       rayDirection = {d3.x, d3.y, d3.z};
     } else {
       rayDirection = dir;
     }
-    const float2 hv = __ldcs(&p.pool.hit[s]);
+    const float4 hv = __ldcs(&p.pool.hit[s]);
     const uint4 meta = __ldcs(&p.pool.meta[s]);
-    const float2 wr = __ldcs(&p.pool.wr[s]);  // all pool loads are issued before the gathers
     idx = (uint64_t)meta.x | ((uint64_t)meta.y << 32);
     numReflections = meta.z;
     boundaryHits = meta.w & 0x7fffffffu;
     hitFromBack = (meta.w >> 31) != 0u;
-    w = wr.x;
-    rs = __float_as_uint(wr.y);
-    const uint32_t hw = __float_as_uint(hv.y);
-    finish = shadeHit<D, GEO, EXT, Q>(p, r, hv.x, hitWordPrim(hw), hitWordGeom(hw), c);
+    w = __ldcs(&p.pool.weight[s]);
+    rs = __ldcs(&p.pool.rng[s]);  // issued with the other pool loads, not after the neighbour gathers
+    finish = shadeHit<D, GEO, EXT, Q>(p, r, hv.x, __float_as_uint(hv.y), __float_as_uint(hv.z), c);
   }
 
   // ---- regenerate finished slots; write survivors back (in place, or appended to
   // the other pool when compacting the tail) ----------------------------------------
   const bool regen = regenerate<D>(p, live && finish, idx, rng, org, rayDirection, dir);
   const bool survive = live && (!finish || regen);
-  // the boundary hit of the ray that goes on (known already after a reflection's sky test)
-  if (survive && !(!finish && bhValid))
-    bh = boundaryTest(sc, org, dir);
-  // the stream's next block: as loaded, unless draws were taken
-  const uint32_t rngBlock = (rngLoaded || finish) ? rng.save() : rs;
   if (!p.compact) {
     if (live) {
-      if (!finish)
-        storeRay<D>(p.pool, s, org, dir, rayDirection, w, rngBlock, idx, numReflections,
-                    boundaryHits, hitFromBack, bh);
-      else if (regen)
-        storeRay<D>(p.pool, s, org, dir, rayDirection, 1.f, rngBlock, idx, 0u, 0u, false, bh);
-      else
-        storeEmptySlot(p.pool, s);
+      if (!finish) {
+        __stcs(&p.pool.od0[s], make_float4(org.x, org.y, org.z, dir.x));
+        __stcs(&p.pool.od1[s], make_float2(dir.y, dir.z));
+        __stcs(&p.pool.meta[s], make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), numReflections,
+                                           boundaryHits | (hitFromBack ? 0x80000000u : 0u)));
+        __stcs(&p.pool.weight[s], w);
+        if (rngLoaded)  // draws were taken from the stream
+          __stcs(&p.pool.rng[s], rng.save());
+        if (D == 2)
+          __stcs(&p.pool.dir3[s],
+                 make_float4(rayDirection.x, rayDirection.y, rayDirection.z, 0.f));
+      } else if (regen) {
+        storeRay<D>(p.pool, s, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
+      } else {
+        p.pool.od0[s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
+      }
+      if (survive) {
+        if (!finish && bhValid)  // the boundary hit of this ray is known already
+          __stcs(&p.pool.hit[s], make_float4(bh.t, __uint_as_float(bh.prim),
+                                             __uint_as_float(bh.geom), 0.f));
+        else
+          storeBoundaryHit(sc, p.pool, s, org, dir);
+      }
     }
   } else {
     const unsigned m = __ballot_sync(0xffffffffu, survive);
@@ -1267,12 +1277,19 @@ __global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) 
       base = __shfl_sync(0xffffffffu, base, leader);
       if (survive) {
         const uint32_t dst = base + __popc(m & ((1u << ln) - 1u));
-        if (!finish)
-          storeRay<D>(p.poolOut, dst, org, dir, rayDirection, w, rngBlock, idx, numReflections,
-                      boundaryHits, hitFromBack, bh);
+        if (!finish) {
+          if (!rngLoaded)
+            rng.load(rs, p.seed, p.stream, idx);
+          storeRay<D>(p.poolOut, dst, org, dir, rayDirection, w, rng, idx, numReflections,
+                      boundaryHits, hitFromBack);
+        } else {
+          storeRay<D>(p.poolOut, dst, org, dir, rayDirection, 1.f, rng, idx, 0u, 0u, false);
+        }
+        if (!finish && bhValid)
+          __stcs(&p.poolOut.hit[dst], make_float4(bh.t, __uint_as_float(bh.prim),
+                                                  __uint_as_float(bh.geom), 0.f));
         else
-          storeRay<D>(p.poolOut, dst, org, dir, rayDirection, 1.f, rngBlock, idx, 0u, 0u, false,
-                      bh);
+          storeBoundaryHit(sc, p.poolOut, dst, org, dir);
       }
     }
   }
@@ -1355,11 +1372,12 @@ __global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ TraceP
   const uint32_t numSlots = *p.slotCount;
   Tally c = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   unsigned wNodes = 0, wPrims = 0;
-  float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u)), b = a;
+  float4 a = make_float4(0.f, 0.f, 0.f, __uint_as_float(0x7fc00000u));
   if (s < numSlots)
-    ldcs256(p.pool.ray + 2 * (size_t)s, a, b);
+    a = __ldcs(&p.pool.od0[s]);
   if (!slotEmpty(a)) {
     RayState r;
+    const float2 b = __ldcs(&p.pool.od1[s]);
     r.org = {a.x, a.y, a.z};
     r.dir = {a.w, b.x, b.y};
     if (D == 2) {
@@ -1368,20 +1386,20 @@ __global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ TraceP
     } else {
       r.rayDirection = r.dir;
     }
+    const float4 hv = __ldcs(&p.pool.hit[s]);
     const uint4 meta = __ldcs(&p.pool.meta[s]);
-    const float2 wr = __ldcs(&p.pool.wr[s]);
     r.idx = (uint64_t)meta.x | ((uint64_t)meta.y << 32);
     r.numReflections = meta.z;
     r.boundaryHits = meta.w & 0x7fffffffu;
     r.hitFromBack = (meta.w >> 31) != 0u;
-    r.w = wr.x;
-    r.rs = __float_as_uint(wr.y);
+    r.w = __ldcs(&p.pool.weight[s]);
+    r.rs = __ldcs(&p.pool.rng[s]);
     r.rngLoaded = false;
     r.rng.init(0, 0, 0);
-    r.bhValid = true;  // the ray record holds the ray's boundary hit
-    r.bh.t = b.z;
-    r.bh.prim = r.bh.orig = hitWordPrim(__float_as_uint(b.w));
-    r.bh.geom = hitWordGeom(__float_as_uint(b.w));
+    r.bhValid = true;  // the pool holds the ray's boundary hit
+    r.bh.t = hv.x;
+    r.bh.prim = r.bh.orig = __float_as_uint(hv.y);
+    r.bh.geom = __float_as_uint(hv.z);
     for (;;) {
       if (!r.bhValid)
         r.bh = boundaryTest(sc, r.org, r.dir);
@@ -1567,7 +1585,9 @@ __global__ void debugLoadRaysKernel(DeviceScene sc, RayPool pool, const float *r
     return;
   V3 org = {rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]};
   V3 dir = {rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]};
-  storeRayRecord(pool, i, org, dir, boundaryTest(sc, org, dir));
+  pool.od0[i] = make_float4(org.x, org.y, org.z, dir.x);
+  pool.od1[i] = make_float2(dir.y, dir.z);
+  storeBoundaryHit(sc, pool, i, org, dir);
 }
 cudaError_t launchDebugLoadRays(const DeviceScene &sc, const RayPool &pool, const float *rays,
                                 uint32_t m, cudaStream_t s) {
@@ -1582,11 +1602,10 @@ __global__ void debugReadHitsKernel(DeviceScene sc, RayPool pool, uint32_t m, ui
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m)
     return;
-  const float4 a = pool.ray[2 * (size_t)i], b4 = pool.ray[2 * (size_t)i + 1];
-  const float2 b = make_float2(b4.x, b4.y);
-  const float2 hv = pool.hit[i];
-  const uint32_t hprim = hitWordPrim(__float_as_uint(hv.y)),
-                 hgeom = hitWordGeom(__float_as_uint(hv.y));
+  const float4 a = pool.od0[i];
+  const float2 b = pool.od1[i];
+  const float4 hv = pool.hit[i];
+  const uint32_t hprim = __float_as_uint(hv.y), hgeom = __float_as_uint(hv.z);
   geom[i] = hgeom;
   prim[i] = hgeom == VR_INVALID_ID ? VR_INVALID_ID : (hgeom == 0u ? hprim : sortedToOrig[hprim]);
   t[i] = hv.x;
