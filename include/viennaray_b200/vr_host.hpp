@@ -29,6 +29,7 @@
 #include <memory>
 #include <random>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -405,6 +406,42 @@ public:
     return true;
   }
 };
+
+// ---- the data-only particle of the reference's own GPU tracer ----------------------------
+// rayParticle.hpp:208-218 (viennaray::gpu::Particle, behind VIENNARAY_USE_GPU there): sticking,
+// sticking by material ID, cosine exponent of the source, optional direction.  A caller that
+// describes its particles this way gets the device particle from makeParticle(); the direction
+// goes to Trace::setPrimaryDirection as in the reference's CPU interface.
+namespace gpu {
+template <typename T> struct Particle {
+  std::string name;
+  std::vector<std::string> dataLabels;
+
+  T sticking = 1.;
+  std::unordered_map<int, T> materialSticking;
+  T cosineExponent = 1.;
+
+  bool useCustomDirection = false;
+  Vec3D<T> direction = {0., 0., -1.0};
+};
+
+/// Diffuse device particle of a gpu::Particle.  Materials missing from the map keep the
+/// particle's own sticking (raygTrace.hpp:174-184 builds the same table); material IDs are
+/// the table's indices, so they must be non-negative.
+template <typename NumericType, int D>
+std::unique_ptr<AbstractParticle<NumericType>> makeParticle(const Particle<NumericType> &p) {
+  int maxId = -1;
+  for (auto const &kv : p.materialSticking)
+    maxId = std::max(maxId, kv.first);
+  std::vector<float> table(static_cast<std::size_t>(maxId + 1), static_cast<float>(p.sticking));
+  for (auto const &kv : p.materialSticking)
+    if (kv.first >= 0)
+      table[static_cast<std::size_t>(kv.first)] = static_cast<float>(kv.second);
+  return std::make_unique<MaterialStickingParticle<NumericType, D>>(
+      VR_PARTICLE_DIFFUSE, p.sticking, std::move(table), p.cosineExponent,
+      p.dataLabels.empty() ? (p.name.empty() ? std::string("flux") : p.name) : p.dataLabels[0]);
+}
+} // namespace gpu
 
 // ---- sources (raySource.hpp:10-19) -------------------------------------------
 template <typename NumericType> class Source {

@@ -1,5 +1,5 @@
 """Experiment: do the traverse and the shade kernel of two independent traces overlap on one GPU when
-each is capped to part of an SM (VR_TRAV_CAP blocks/SM, VR_SHADE_SMEM_PAD bytes)?  Runs the C4 step
+each is capped to part of an SM (VR_TRAV_CAP blocks/SM, VR_SHADE_SMEM_PAD bytes: knobs of commits a29880a..1ab9da5, removed since)?  Runs the C4 step
 on one context, then on two contexts from two host threads, and prints the aggregate rates."""
 import sys, time, threading
 import numpy as np

@@ -281,6 +281,19 @@ static void testHostHelpers() {
   vr_particle_desc pd{};
   VC_TEST_ASSERT(mp->clone()->deviceParticle(pd) && pd.numMaterials == 2 &&
                  pd.stickingByMaterial[1] == 0.6f && pd.sticking == 0.1f);
+
+  // the data-only particle of the reference's GPU tracer (rayParticle.hpp:208-218)
+  gpu::Particle<float> gp;
+  gp.name = "neutral";
+  gp.sticking = 0.2f;
+  gp.cosineExponent = 3.f;
+  gp.materialSticking = {{2, 0.9f}, {0, 0.4f}};
+  auto dp = gpu::makeParticle<float, 3>(gp);
+  vr_particle_desc gd{};
+  VC_TEST_ASSERT(dp->deviceParticle(gd) && gd.kind == VR_PARTICLE_DIFFUSE && gd.numMaterials == 3 &&
+                 gd.stickingByMaterial[0] == 0.4f && gd.stickingByMaterial[1] == 0.2f &&
+                 gd.stickingByMaterial[2] == 0.9f && gd.sourcePower == 3.f);
+  VC_TEST_ASSERT(dp->getLocalDataLabels()[0] == "neutral");
 }
 
 // ------------------------------------------------------------------ device blocks

@@ -22,7 +22,6 @@
 // to running each ray to completion on its own (per-ray counter RNG, fixed
 // point flux sums), which is what the CPU oracle does.
 #include "vr_device.cuh"
-#include <cstdlib>
 
 namespace vr {
 
@@ -723,15 +722,6 @@ static cudaError_t launchTraverseT(const TraceParams &p, int numSMs, cudaStream_
   }
   unsigned want = (p.numSlots + (unsigned)T - 1u) / (unsigned)T;
   unsigned grid = (unsigned)(numSMs * perSM);
-  {  // experiment knob: resident traverse blocks per SM (co-residency with another kernel)
-    static int cap = -1;
-    if (cap < 0) {
-      const char *e = getenv("VR_TRAV_CAP");
-      cap = e ? atoi(e) : 0;
-    }
-    if (cap > 0 && cap < perSM)
-      grid = (unsigned)(numSMs * cap);
-  }
   if (want < grid)
     grid = want;
   traverseKernel<GEO, WIDE, COUNT, TOP><<<grid, T, smem, s>>>(p);
@@ -1486,22 +1476,13 @@ cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int com
 }
 
 template <int EXT> static void launchShadeExt(const TraceParams &p, unsigned grid, cudaStream_t s) {
-  // experiment knob: dynamic shared memory padding that limits the shade kernel's resident
-  // blocks per SM (co-residency with the traverse kernel of another stream)
-  static int pad = -1;
-  if (pad < 0) {
-    const char *e = getenv("VR_SHADE_SMEM_PAD");
-    pad = e ? atoi(e) : 0;
-    if (pad > 0)
-      cudaFuncSetAttribute(shadeKernel<3, 0, EXT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-  }
   if (p.scene.geoType == 0) {
     if (p.scene.D == 2)
       shadeKernel<2, 0, EXT, 0><<<grid, 256, 0, s>>>(p);
     else if (!EXT && p.spreadQ)  // neighbour spread queued for spreadKernel
       shadeKernel<3, 0, 0, 1><<<grid, 256, 0, s>>>(p);
     else
-      shadeKernel<3, 0, EXT, 0><<<grid, 256, pad, s>>>(p);
+      shadeKernel<3, 0, EXT, 0><<<grid, 256, 0, s>>>(p);
   } else {
     if (p.scene.D == 2)
       shadeKernel<2, 1, EXT, 0><<<grid, 256, 0, s>>>(p);
