@@ -166,7 +166,25 @@ def traffic_capture(config_name):
     return best
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else a library
+    prints on fd 1 while the bench runs (NCCL's version banner, for one) was sent to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
@@ -227,7 +245,7 @@ def main():
                                  "intersector (Embree absent)" if kind == "reference" else sample},
                 "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ CUDA arm
@@ -512,7 +530,7 @@ def main():
         rate, kind, cores, sample, _ = cpu_reference_rate(wl, args.cpu_seconds)
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": kind,
                                 "sample": sample}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

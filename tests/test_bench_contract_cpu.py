@@ -16,7 +16,9 @@ def test_reference_arm_json_line():
                           "--steps", "1", "--warmup", "0", "--slices", "20", "--cpu-seconds", "1"],
                          capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
-    line = json.loads(res.stdout.strip().splitlines()[-1])
+    lines = res.stdout.strip().splitlines()
+    assert len(lines) == 1, "stdout must carry the JSON line and nothing else"
+    line = json.loads(lines[-1])
     assert line["impl"] == "reference" and line["metric"] == "rays/s" and line["unit"] == "rays/s"
     assert line["higher_is_better"] is True and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port")
