@@ -22,6 +22,7 @@
 // to running each ray to completion on its own (per-ray counter RNG, fixed
 // point flux sums), which is what the CPU oracle does.
 #include "vr_device.cuh"
+#include <mutex>
 
 namespace vr {
 
@@ -703,22 +704,30 @@ static cudaError_t launchTraverseT(const TraceParams &p, int numSMs, cudaStream_
   constexpr int T = TravShape<TOP>::threads;
   // the table is sized per scene; the launch asks for what this scene's table needs
   const size_t smem = TOP ? (size_t)p.scene.topCount * 32u : 0u;
-  static int perSM = 0;
+  // resident blocks per SM of this instantiation (cached; the lanes of a trace and the
+  // devices of a multi-device context launch from several host threads)
+  static std::mutex mu;
+  static int cachedPerSM = 0;
   static size_t smemFor = ~(size_t)0;
-  if (perSM == 0 || smemFor != smem) {
-    cudaError_t e = cudaSuccess;
-    if (TOP)
-      e = cudaFuncSetAttribute(traverseKernel<GEO, WIDE, COUNT, TOP>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(VR_TOP_MAX * 32u));
-    if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &perSM, traverseKernel<GEO, WIDE, COUNT, TOP>, T, smem);
-    if (e != cudaSuccess)
-      return e;
-    if (perSM < 1)
-      perSM = 1;
-    smemFor = smem;
+  int perSM;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cachedPerSM == 0 || smemFor != smem) {
+      cudaError_t e = cudaSuccess;
+      int v = 0;
+      if (TOP)
+        e = cudaFuncSetAttribute(traverseKernel<GEO, WIDE, COUNT, TOP>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(VR_TOP_MAX * 32u));
+      if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &v, traverseKernel<GEO, WIDE, COUNT, TOP>, T, smem);
+      if (e != cudaSuccess)
+        return e;
+      cachedPerSM = v < 1 ? 1 : v;
+      smemFor = smem;
+    }
+    perSM = cachedPerSM;
   }
   unsigned want = (p.numSlots + (unsigned)T - 1u) / (unsigned)T;
   unsigned grid = (unsigned)(numSMs * perSM);
