@@ -174,6 +174,21 @@ int vr_flux_download_fixed(vr_ctx *ctx, uint64_t *fluxOut);
  * neighbourhood (rayTraceDisk.hpp:146-193, numNeighbors == 1). */
 int vr_flux_postprocess(vr_ctx *ctx, int particle, const float *areas, float normFactor,
                         int smooth, float *fluxOut);
+/* The general form: normalizeFlux(SOURCE | MAX) followed by smoothFlux(numNeighbors), all on
+ * the device, float flux of one particle in the caller's primitive order.
+ *   VR_NORM_SOURCE  flux[i] *= float(normFactor) / areas[i], normFactor = sourceArea / numRays
+ *                   (rayTraceDisk.hpp:121-138, rayTraceTriangle.hpp:110-126)
+ *   VR_NORM_MAX     disks: flux[i] = flux[i] * ((normFactor / areas[i]) / max(flux)) in double,
+ *                   normFactor = radius * radius * pi (rayTraceDisk.hpp:110-118; the argument is
+ *                   ignored for triangles: flux[i] /= max(flux) * areas[i], rayTraceTriangle.hpp:
+ *                   99-107)
+ *   smoothNeighbors 0: none; 1: the geometry's own neighbourhood; k > 1: a neighbourhood of
+ *                   k * 2 * diskRadius over the disk centres, built on the device
+ *                   (rayTraceDisk.hpp:146-193).  Disks only; ignored for triangles. */
+enum { VR_NORM_NONE = 0, VR_NORM_SOURCE = 1, VR_NORM_MAX = 2 };
+int vr_flux_postprocess_ex(vr_ctx *ctx, int particle, const float *areas, int normalization,
+                           double normFactor, int smoothNeighbors, float diskRadius,
+                           float *fluxOut);
 /* cudaStream_t of the context (for event timing by the caller) */
 void *vr_ctx_stream(vr_ctx *ctx);
 int vr_ctx_synchronize(vr_ctx *ctx);

@@ -1142,6 +1142,29 @@ public:
     return std::vector<NumericType>(out.begin(), out.end());
   }
 
+  /// The general form: normalizeFlux(norm) followed by smoothFlux(numNeighbors) of particle
+  /// `particle` of the last apply(), on the device (vr_flux_postprocess_ex); numNeighbors = 0:
+  /// no smoothing, > 1: a wider neighbourhood built on the device.  Empty vector on error.
+  [[nodiscard]] std::vector<NumericType> getDeviceFlux(NormalizationType norm, int numNeighbors,
+                                                       int particle = 0) {
+    std::vector<float> out(numPoints()), areas;
+    if (!this->ctx_ || (norm == NormalizationType::SOURCE && !this->haveSource_))
+      return {};
+    computeDiskAreas();
+    areas.assign(diskAreas_.begin(), diskAreas_.end());
+    const bool max = norm == NormalizationType::MAX;
+    // the factors as the reference forms them (rayTraceDisk.hpp:111,129-133)
+    const double factor =
+        max ? static_cast<double>(static_cast<NumericType>(diskRadius_ * diskRadius_)) * M_PI
+            : static_cast<double>(static_cast<float>(this->sourceArea_) /
+                                  static_cast<float>(this->totalRays()));
+    if (vr_flux_postprocess_ex(this->ctx_, particle, areas.data(), max ? VR_NORM_MAX : VR_NORM_SOURCE,
+                               factor, numNeighbors, static_cast<float>(diskRadius_),
+                               out.data()) != VR_OK)
+      return {};
+    return std::vector<NumericType>(out.begin(), out.end());
+  }
+
   // introspection used by the parity tests (GeometryDisk getters)
   [[nodiscard]] std::size_t numPoints() const { return xyzr_.size() / 4; }
   [[nodiscard]] const std::vector<double> &getDiskAreas() {

@@ -103,6 +103,8 @@ def oracle_lib():
         L.vro_boundary_process_hit.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_uint32, C.c_float]
         L.vro_normalize_flux_source.argtypes = [_vp, _vp, C.c_uint64, _vp]
         L.vro_smooth_flux.argtypes = [_vp, _vp]
+        L.vro_normalize_flux_max.argtypes = [_vp, _vp, _vp]
+        L.vro_smooth_flux_k.argtypes = [_vp, C.c_int, _vp]
         L.vro_philox4x32.argtypes = [C.c_uint32] * 6 + [_vp]
         L.vro_math_sincos2pi.argtypes = [_vp, C.c_uint32, _vp, _vp]
         L.vro_math_pow.argtypes = [_vp, C.c_float, C.c_uint32, _vp]
@@ -307,9 +309,15 @@ class OracleScene:
         self.L.vro_normalize_flux_source(self.h, _p(areas), num_rays, _p(flux))
         return flux
 
-    def smooth_flux(self, flux):
+    def smooth_flux(self, flux, k=1):
         flux = np.ascontiguousarray(flux, np.float32).copy()
-        self.L.vro_smooth_flux(self.h, _p(flux))
+        self.L.vro_smooth_flux_k(self.h, int(k), _p(flux))
+        return flux
+
+    def normalize_flux_max(self, flux, areas):
+        flux = np.ascontiguousarray(flux, np.float32).copy()
+        areas = np.ascontiguousarray(areas, np.float32)
+        self.L.vro_normalize_flux_max(self.h, _p(areas), _p(flux))
         return flux
 
 
@@ -358,6 +366,22 @@ def ref_trace_triangle(verts, tris, grid_delta, bc, source_dir, kind, sticking, 
                                   C.byref(sec))
     assert rc == 0
     return flux, info, sec.value
+
+
+def ref_post_disk(D, points, normals, grid_delta, bc, source_dir, flux, norm=0, smooth=0,
+                  rays_fixed=1000):
+    """The reference's normalizeFlux (norm: 1 SOURCE, 2 MAX) / smoothFlux(smooth) of `flux`."""
+    L = ref_lib()
+    points = np.ascontiguousarray(points, np.float32)
+    normals = np.ascontiguousarray(normals, np.float32)
+    out = np.ascontiguousarray(flux, np.float32).copy()
+    bc = (C.c_int * 3)(*(list(bc) + [IGNORE] * 3)[:3])
+    L.ref_post_disk.argtypes = [C.c_int, _vp, _vp, C.c_uint32, C.c_float, C.POINTER(C.c_int),
+                                C.c_int, C.c_uint64, C.c_int, C.c_int, _vp]
+    rc = L.ref_post_disk(D, _p(points), _p(normals), len(points), grid_delta, bc, source_dir,
+                         rays_fixed, norm, smooth, _p(out))
+    assert rc == 0
+    return out
 
 
 def ref_neighbors(D, points, distance, cap=64):

@@ -195,9 +195,54 @@ int traceDisk(const float *points, const float *normals, uint32_t n, float gridD
   return 0;
 }
 
+// The reference's own post-processing of a GIVEN flux vector: TraceDisk::normalizeFlux(norm)
+// and smoothFlux(k) (rayTraceDisk.hpp:103-193) after a short apply() that initialises the
+// geometry (disk areas, neighbourhood).  norm: 0 none, 1 SOURCE, 2 MAX.
+template <int D>
+int postDisk(const float *points, const float *normals, uint32_t n, float gridDelta, const int *bc,
+             int sourceDir, uint64_t raysFixed, int norm, int smooth, float *flux) {
+  std::vector<Vec3D<float>> pts(n), nrm(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    pts[i] = {points[3 * i], points[3 * i + 1], points[3 * i + 2]};
+    nrm[i] = {normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]};
+  }
+  BoundaryCondition conds[D];
+  for (int i = 0; i < D; ++i)
+    conds[i] = static_cast<BoundaryCondition>(bc[i]);
+  auto particle = makeParticle<D>(ParticleDesc{0, 1.f, 1.f, 0.f});
+  TraceDisk<float, D> tracer;
+  tracer.setGeometry(pts, nrm, gridDelta);
+  tracer.setBoundaryConditions(conds);
+  tracer.setSourceDirection(static_cast<TraceDirection>(sourceDir));
+  tracer.setParticleType(particle);
+  tracer.setNumberOfRaysFixed(raysFixed);
+  tracer.setRngSeed(1);
+  tracer.apply();
+  std::vector<float> f(flux, flux + n);
+  if (norm == 1)
+    tracer.normalizeFlux(f, NormalizationType::SOURCE);
+  else if (norm == 2)
+    tracer.normalizeFlux(f, NormalizationType::MAX);
+  if (smooth > 0)
+    tracer.smoothFlux(f, smooth);
+  std::memcpy(flux, f.data(), sizeof(float) * n);
+  return 0;
+}
+
 } // namespace
 
 extern "C" {
+
+// flux (n floats) in and out: the reference's normalizeFlux / smoothFlux on it
+int ref_post_disk(int D, const float *points, const float *normals, uint32_t n, float gridDelta,
+                  const int *bc, int sourceDir, uint64_t raysFixed, int norm, int smooth,
+                  float *flux) {
+  if (D == 3)
+    return postDisk<3>(points, normals, n, gridDelta, bc, sourceDir, raysFixed, norm, smooth, flux);
+  if (D == 2)
+    return postDisk<2>(points, normals, n, gridDelta, bc, sourceDir, raysFixed, norm, smooth, flux);
+  return 1;
+}
 
 int ref_max_threads() { return omp_get_max_threads(); }
 void ref_set_threads(int n) { omp_set_num_threads(n); }

@@ -1336,6 +1336,48 @@ void vro_smooth_flux(const vro_scene *s, float *flux) {
   free(old);
 }
 
+/* normalizeFlux(MAX): rayTraceDisk.hpp:110-118 (disks: the factor is formed in double,
+ * diskRadius_ * diskRadius_ * M_PI) and rayTraceTriangle.hpp:99-107 (triangles: float) */
+void vro_normalize_flux_max(const vro_scene *s, const float *areas, float *flux) {
+  float maxv = flux[0];
+  for (uint32_t i = 1; i < s->n; ++i)
+    if (flux[i] > maxv)
+      maxv = flux[i];
+  if (s->geoType == 0) {
+    const double total = (double)(s->radius * s->radius) * 3.14159265358979323846;
+    for (uint32_t i = 0; i < s->n; ++i)
+      flux[i] = (float)((double)flux[i] * ((total / (double)areas[i]) / (double)maxv));
+  } else {
+    for (uint32_t i = 0; i < s->n; ++i)
+      flux[i] = flux[i] / (maxv * areas[i]);
+  }
+}
+
+/* rayTraceDisk.hpp:146-193 with numNeighbors = k > 1: a new neighbourhood of distance
+ * k * 2 * radius over the points (init<3>: all three axes), rows in ascending index order */
+void vro_smooth_flux_k(const vro_scene *s, int k, float *flux) {
+  if (k <= 1) {
+    vro_smooth_flux(s, flux);
+    return;
+  }
+  vro_scene t;
+  memset(&t, 0, sizeof(t));
+  t.D = 3;
+  t.n = s->n;
+  memcpy(t.geoMin, s->geoMin, sizeof(t.geoMin));
+  memcpy(t.geoMax, s->geoMax, sizeof(t.geoMax));
+  float *pts = (float *)malloc(sizeof(float) * 3 * (s->n + 1));
+  for (uint32_t i = 0; i < s->n; ++i)
+    for (int a = 0; a < 3; ++a)
+      pts[3 * i + a] = s->disk[4 * i + a];
+  build_neighbors(&t, pts, (float)k * 2 * s->radius);
+  t.normal = s->normal;
+  vro_smooth_flux(&t, flux);
+  free(t.nbOff);
+  free(t.nbIdx);
+  free(pts);
+}
+
 /* m reflections of (rayDir, normal) with ray streams idx .. idx+m-1 */
 void vro_reflect(int kind, int D, const float *rayDir, const float *normal, float coneMinAngle,
                  uint32_t seed, uint64_t idx, uint32_t m, float *out) {

@@ -98,6 +98,10 @@ int vro_boundary_process_hit(const vro_scene *s, float *org, float *rayDir3, flo
 void vro_normalize_flux_source(const vro_scene *s, const float *areas, uint64_t numRays,
                                float *flux);
 void vro_smooth_flux(const vro_scene *s, float *flux);
+/* normalizeFlux(MAX), rayTraceDisk.hpp:110-118 / rayTraceTriangle.hpp:99-107 */
+void vro_normalize_flux_max(const vro_scene *s, const float *areas, float *flux);
+/* smoothFlux(flux, k), rayTraceDisk.hpp:146-193 (k > 1: neighbourhood of k * 2 * radius) */
+void vro_smooth_flux_k(const vro_scene *s, int k, float *flux);
 
 /* building blocks exposed for bit-parity unit tests */
 void vro_philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -356,6 +356,15 @@ static void testTraceInterface(const std::string &out) {
     for (std::size_t i = 0; i < devFlux.size(); ++i)
       VC_TEST_ASSERT_ISCLOSE(devFlux[i], hostFlux[i], 1e-5 * (1 + std::fabs(hostFlux[i])));
   }
+  {  // the general device call == host normalizeFlux(MAX) + smoothFlux(2) (wider neighbourhood)
+    auto hostFlux = flux;
+    rayTracer.normalizeFlux(hostFlux, NormalizationType::MAX);
+    rayTracer.smoothFlux(hostFlux, 2);
+    auto devFlux = rayTracer.getDeviceFlux(NormalizationType::MAX, 2);
+    VC_TEST_ASSERT(devFlux.size() == hostFlux.size());
+    for (std::size_t i = 0; i < devFlux.size(); ++i)
+      VC_TEST_ASSERT_ISCLOSE(devFlux[i], hostFlux[i], 1e-5 * (1 + std::fabs(hostFlux[i])));
+  }
   rayTracer.normalizeFlux(flux);
   rayTracer.smoothFlux(flux, 2);
   double mean = 0;

@@ -227,6 +227,38 @@ def test_flux_postprocess_on_device(pair):
     assert (got.view(np.uint32) == expect.view(np.uint32)).all()
 
 
+def test_flux_postprocess_max_and_wide_smoothing(pair):
+    """normalizeFlux(MAX) (rayTraceDisk.hpp:110-118 in double, rayTraceTriangle.hpp:99-107) and
+    smoothFlux(k) with k > 1 -- a neighbourhood of k * 2 * radius built on the device
+    (rayTraceDisk.hpp:160-168) -- against the oracle's restatement, bit for bit."""
+    c, orc, ctx, src, st = pair
+    num = 60000
+    ctx.trace_device(src, [common.gpu_particle(c)], host.config(num, SEED), sync=True)
+    fo, _ = orc.trace(common.oracle_particle(c), orc.config(num, SEED))
+    raw = (fo / po.FLUX_SCALE).astype(np.float32)
+    assert (ctx.flux_postprocess_ex() == raw).all()
+    rng = np.random.default_rng(9)
+    areas = (0.5 + rng.random(orc.n)).astype(np.float32)
+    r = host.disk_radius(c["grid_delta"], c["D"]) if c["geo"] == "disk" else np.float32(0)
+    total = float(np.float32(r * r)) * np.pi  # diskRadius_ * diskRadius_ * M_PI
+    expect = orc.normalize_flux_max(raw, areas)
+    got = ctx.flux_postprocess_ex(0, areas, capi.NORM_MAX, total)
+    assert (got.view(np.uint32) == expect.view(np.uint32)).all()
+    if c["geo"] != "disk":
+        # triangles are not smoothed (rayTraceTriangle.hpp has no neighbourhood)
+        assert (ctx.flux_postprocess_ex(0, areas, capi.NORM_MAX, total, 2, 1.0) == expect).all()
+        return
+    for k in (1, 2, 3):
+        e = orc.smooth_flux(expect, k)
+        g = ctx.flux_postprocess_ex(0, areas, capi.NORM_MAX, total, k, r)
+        assert (g.view(np.uint32) == e.view(np.uint32)).all(), "k = %d" % k
+    # SOURCE through the general call equals the first interface
+    norm = 0.37
+    a = ctx.flux_postprocess(0, areas, norm, smooth=True)
+    b = ctx.flux_postprocess_ex(0, areas, capi.NORM_SOURCE, float(np.float32(norm)), 1, r)
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+
+
 @pytest.mark.parametrize("name", ["disk3D", "disk2D", "trench", "holes", "plane"])
 def test_neighbor_build_on_device(name):
     """PointNeighborhood on the device == host build == oracle, and a trace

@@ -233,6 +233,30 @@ def test_smoothing_known_answer():
     assert np.allclose(out, [1, 1, 1, 0, 0, 0], atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["disk3D", "trench"])
+def test_postprocessing_equals_reference(name):
+    """normalizeFlux(MAX) and smoothFlux(k), k = 1, 2, 3, of the oracle against the reference's
+    own TraceDisk methods on the same flux vector (rayTraceDisk.hpp:103-193).  MAX is formed in
+    double on both sides: bit-equal.  The smoothing sums run over the same neighbour sets in a
+    different row order (the oracle's rows are ascending): float tolerance."""
+    if not po.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    c = common.case(name)
+    orc = common.make_oracle(c)
+    rng = np.random.default_rng(11)
+    flux = (rng.random(orc.n) * 50).astype(F)
+    areas = po.ref_disk_areas(c["D"], c["points"], c["normals"], c["grid_delta"], c["bc"],
+                              c["source_dir"])
+    args = (c["D"], c["points"], c["normals"], c["grid_delta"], c["bc"], c["source_dir"])
+    ref = po.ref_post_disk(*args, flux, norm=2)
+    mine = orc.normalize_flux_max(flux, areas)
+    assert (ref.view(np.uint32) == mine.view(np.uint32)).all()
+    for k in (1, 2, 3):
+        ref = po.ref_post_disk(*args, flux, norm=0, smooth=k)
+        mine = orc.smooth_flux(flux, k)
+        assert np.allclose(ref, mine, rtol=2e-6, atol=1e-6), "k = %d" % k
+
+
 # --------------------------------------------------------------------------------------
 # tests/rngSeed/rngSeed.cpp:48-51 and tests/traceInterface/traceInterface.cpp:67
 # --------------------------------------------------------------------------------------

@@ -22,12 +22,15 @@ EXPORTS = [
     "vr_scene_set_triangles", "vr_scene_build_neighbors", "vr_scene_get_neighbors",
     "vr_scene_set_boundary", "vr_source_set_grid", "vr_scene_commit", "vr_trace",
     "vr_trace_device", "vr_flux_device", "vr_flux_download", "vr_flux_download_fixed",
-    "vr_flux_postprocess",
+    "vr_flux_postprocess", "vr_flux_postprocess_ex",
     "vr_ctx_stream", "vr_ctx_synchronize", "vr_last_kernel_ms", "vr_last_launch_count", "vr_build_neighbors", "vr_free",
     "vr_debug_intersect", "vr_debug_source_rays", "vr_debug_math", "vr_debug_philox",
     "vr_debug_reflect", "vr_debug_bvh_stats", "vr_debug_work_counters", "vr_debug_l2_read_bandwidth", "vr_debug_phase_timing",
     "vr_debug_phase_ms",
 ]
+
+
+NORM_NONE, NORM_SOURCE, NORM_MAX = 0, 1, 2  # vr_flux_postprocess_ex
 
 
 class SourceDesc(C.Structure):
@@ -108,6 +111,8 @@ def lib():
         L.vr_flux_download.argtypes = [_vp, _vp, _vp]
         L.vr_flux_download_fixed.argtypes = [_vp, _vp]
         L.vr_flux_postprocess.argtypes = [_vp, C.c_int, _vp, C.c_float, C.c_int, _vp]
+        L.vr_flux_postprocess_ex.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double, C.c_int,
+                                             C.c_float, _vp]
         L.vr_ctx_stream.restype = _vp
         L.vr_ctx_stream.argtypes = [_vp]
         L.vr_ctx_synchronize.argtypes = [_vp]
@@ -296,6 +301,17 @@ class Context:
         out = np.zeros(self.n, np.float32)
         self._ck(self.L.vr_flux_postprocess(self.h, particle, _p(areas), np.float32(norm_factor),
                                             1 if smooth else 0, _p(out)))
+        return out
+
+    def flux_postprocess_ex(self, particle=0, areas=None, normalization=0, norm_factor=1.0,
+                            smooth_neighbors=0, disk_radius=0.0):
+        """normalizeFlux(SOURCE = 1 | MAX = 2) + smoothFlux(smooth_neighbors) on the device."""
+        if areas is not None:
+            areas = np.ascontiguousarray(areas, np.float32)
+        out = np.zeros(self.n, np.float32)
+        self._ck(self.L.vr_flux_postprocess_ex(self.h, particle, _p(areas), int(normalization),
+                                               float(norm_factor), int(smooth_neighbors),
+                                               np.float32(disk_radius), _p(out)))
         return out
 
     def stream(self):

@@ -1610,6 +1610,79 @@ int vr_flux_postprocess(vr_ctx *ctx, int particle, const float *areas, float nor
   return VR_OK;
 }
 
+int vr_flux_postprocess_ex(vr_ctx *ctx, int particle, const float *areas, int normalization,
+                           double normFactor, int smoothNeighbors, float diskRadius,
+                           float *fluxOut) {
+  if (ctx && !ctx->children.empty()) {
+    int rc_ = vr_flux_postprocess_ex(ctx->children[0], particle, areas, normalization, normFactor,
+                                     smoothNeighbors, diskRadius, fluxOut);
+    return rc_ ? childFail(ctx, ctx->children[0], rc_) : VR_OK;
+  }
+  if (!ctx || !fluxOut)
+    return VR_ERR_ARGUMENT;
+  if (!ctx->dFluxOrig || !ctx->resultValid || !ctx->committed)
+    return fail(ctx, VR_ERR_STATE, "vr_flux_postprocess_ex: no trace has run on the current scene");
+  if (particle < 0 || particle >= ctx->numParticles)
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_flux_postprocess_ex: particle index out of range");
+  if (normalization < VR_NORM_NONE || normalization > VR_NORM_MAX ||
+      (normalization != VR_NORM_NONE && !areas))
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_flux_postprocess_ex: normalisation needs the areas");
+  if (smoothNeighbors < 0)
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_flux_postprocess_ex: negative smoothing width");
+  const bool smooth = smoothNeighbors > 0 && ctx->geoType == 0;  // triangles: no smoothing
+  if (smooth && smoothNeighbors == 1 && !ctx->dNbOffO)
+    return fail(ctx, VR_ERR_STATE, "vr_flux_postprocess_ex: the scene has no neighbour lists");
+  if (smooth && smoothNeighbors > 1 && !(diskRadius > 0.f))
+    return fail(ctx, VR_ERR_ARGUMENT, "vr_flux_postprocess_ex: wider smoothing needs the disk radius");
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t n = ctx->n;
+  float *buf = nullptr, *dPts = nullptr;  // buf: areas | tmp | out | maximum
+  uint32_t *dOff = nullptr, *dIdx = nullptr;
+  cudaError_t e = cudaMallocAsync(&buf, sizeof(float) * (3 * (size_t)n + 4), ctx->stream);
+  const uint32_t *off = nullptr, *idx = nullptr;
+  if (e == cudaSuccess && areas)
+    e = stagedCopy(ctx, buf, areas, sizeof(float) * n);
+  if (e == cudaSuccess && smooth) {
+    if (smoothNeighbors == 1) {
+      off = ctx->dNbOffO;
+      idx = ctx->dNbIdxO;
+    } else {
+      // a new neighbourhood of numNeighbors * 2 * radius over the points (rayTraceDisk.hpp:
+      // 160-168, init<3>), built on the device
+      size_t total = 0;
+      e = cudaMallocAsync(&dPts, sizeof(float) * 3 * (size_t)n, ctx->stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(dPts, 3 * sizeof(float), ctx->dXyzr, 4 * sizeof(float),
+                              3 * sizeof(float), n, cudaMemcpyDeviceToDevice, ctx->stream);
+      if (e == cudaSuccess)
+        e = cudaMallocAsync(&dOff, sizeof(uint32_t) * ((size_t)n + 1), ctx->stream);
+      if (e == cudaSuccess)
+        e = buildNeighborsDevice(3, dPts, n, ctx->geoLo, (float)smoothNeighbors * 2 * diskRadius,
+                                 dOff, &dIdx, &total, ctx->stream);
+      off = dOff;
+      idx = dIdx;
+    }
+  }
+  // MAX on triangles divides by max * area (rayTraceTriangle.hpp:99-107)
+  const int mode = normalization == VR_NORM_MAX ? (ctx->geoType == 0 ? 2 : 3) : normalization;
+  if (e == cudaSuccess)
+    e = postprocessFluxEx(ctx->dFluxOrig + (size_t)particle * n, n, areas ? buf : nullptr, mode,
+                          normFactor, ctx->dNxyz, off, idx, buf + n, buf + 2 * (size_t)n,
+                          reinterpret_cast<unsigned int *>(buf + 3 * (size_t)n), ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(fluxOut, buf + 2 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost,
+                        ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  cudaFreeAsync(buf, ctx->stream);
+  cudaFreeAsync(dPts, ctx->stream);
+  cudaFreeAsync(dOff, ctx->stream);
+  cudaFreeAsync(dIdx, ctx->stream);
+  if (e != cudaSuccess)
+    return failCuda(ctx, e, "vr_flux_postprocess_ex");
+  return VR_OK;
+}
+
 int vr_flux_download_fixed(vr_ctx *ctx, uint64_t *fluxOut) {
   if (ctx && !ctx->children.empty())
     {

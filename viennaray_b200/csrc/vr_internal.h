@@ -164,6 +164,10 @@ cudaError_t launchPackTriangles(const float *verts, const uint32_t *tris, const 
 cudaError_t launchGatherPrims(int geoType, const float4 *A, const float4 *B, const float4 *C,
                               const float4 *N, const uint32_t *s2o, uint32_t n, float4 *prim,
                               cudaStream_t s);
+cudaError_t postprocessFluxEx(const unsigned long long *fixedOrig, uint32_t n, const float *areas,
+                              int mode, double factor, const float *nxyz, const uint32_t *off,
+                              const uint32_t *idx, float *tmp, float *out, unsigned int *maxBits,
+                              cudaStream_t s);
 cudaError_t remapNeighbors(const uint32_t *s2o, const uint32_t *offO, const uint32_t *idxO,
                            uint32_t n, uint32_t *o2s, uint32_t *cnt, uint32_t *off, uint32_t *idx,
                            uint32_t *row, cudaStream_t s);

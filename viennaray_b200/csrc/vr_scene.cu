@@ -365,6 +365,58 @@ __global__ void smoothFluxKernel(DeviceScene sc, const float *in, float *out) {
   out[i] = vv / sum;
 }
 
+// ---- the general post-processing (vr_flux_postprocess_ex), all in the caller's order -----------
+// raw sums as floats; their maximum (non-negative floats order like their bits)
+__global__ void fluxRawKernel(const unsigned long long *fixedOrig, uint32_t n, float *out,
+                              unsigned int *maxBits) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  float f = 0.f;
+  if (i < n) {
+    f = (float)((double)fixedOrig[i] * (1.0 / 1073741824.0));
+    out[i] = f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, o));
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(maxBits, __float_as_uint(f));
+}
+// normalizeFlux: 1 SOURCE flux *= factor / area (rayTraceDisk.hpp:121-138); 2 MAX, disks:
+// flux = float(double(flux) * ((factor / area) / max)) with factor = r * r * pi in double
+// (:110-118); 3 MAX, triangles: flux /= max * area (rayTraceTriangle.hpp:99-107)
+__global__ void fluxNormalizeKernel(float *flux, const float *areas, uint32_t n, int mode,
+                                    double factor, const unsigned int *maxBits) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float maxv = __uint_as_float(*maxBits);
+  float f = flux[i];
+  if (mode == 1)
+    f *= (float)factor / areas[i];
+  else if (mode == 2)
+    f = (float)((double)f * ((factor / (double)areas[i]) / (double)maxv));
+  else if (mode == 3)
+    f = f / (maxv * areas[i]);
+  flux[i] = f;
+}
+// smoothFlux over a neighbourhood given as CSR in the caller's order (rayTraceDisk.hpp:170-192)
+__global__ void smoothFluxCsrKernel(const float *nxyz, const uint32_t *off, const uint32_t *idx,
+                                    uint32_t n, const float *in, float *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float nx = nxyz[3 * i], ny = nxyz[3 * i + 1], nz = nxyz[3 * i + 2];
+  float vv = in[i], sum = 1.f;
+  for (uint32_t k = off[i]; k < off[i + 1]; ++k) {
+    const uint32_t j = idx[k];
+    const float w = (nx * nxyz[3 * j] + ny * nxyz[3 * j + 1]) + nz * nxyz[3 * j + 2];
+    if (w > 0.f) {
+      vv += in[j] * w;
+      sum += w;
+    }
+  }
+  out[i] = vv / sum;
+}
 __global__ void unsortFloatKernel(const float *src, const uint32_t *s2o, uint32_t n, float *dst) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n)
@@ -445,6 +497,23 @@ cudaError_t postprocessFlux(const DeviceScene &sc, const unsigned long long *fix
     cur = tmpB;
   }
   unsortFloatKernel<<<(n + 255) / 256, 256, 0, s>>>(cur, s2o, n, outOrig);
+  return cudaGetLastError();
+}
+
+cudaError_t postprocessFluxEx(const unsigned long long *fixedOrig, uint32_t n, const float *areas,
+                              int mode, double factor, const float *nxyz, const uint32_t *off,
+                              const uint32_t *idx, float *tmp, float *out, unsigned int *maxBits,
+                              cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(maxBits, 0, sizeof(unsigned int), s);
+  if (e != cudaSuccess)
+    return e;
+  const unsigned grid = (n + 255) / 256;
+  float *first = off ? tmp : out;
+  fluxRawKernel<<<grid, 256, 0, s>>>(fixedOrig, n, first, maxBits);
+  if (mode && areas)
+    fluxNormalizeKernel<<<grid, 256, 0, s>>>(first, areas, n, mode, factor, maxBits);
+  if (off)
+    smoothFluxCsrKernel<<<grid, 256, 0, s>>>(nxyz, off, idx, n, tmp, out);
   return cudaGetLastError();
 }
 
