@@ -41,6 +41,12 @@ namespace vr {
 #ifndef VR_TRAV_BLOCKS
 #define VR_TRAV_BLOCKS 10  // resident blocks per SM asked of ptxas (caps registers at 48)
 #endif
+#ifndef VR_TRAV_THREADS
+#define VR_TRAV_THREADS 128  // threads per traverse block (the resident warps per SM stay the same)
+#endif
+#ifndef VR_SHADE_THREADS
+#define VR_SHADE_THREADS 256  // threads per shade block
+#endif
 #ifndef VR_TRAV_BLOCKS_WIDE
 #define VR_TRAV_BLOCKS_WIDE 10  // the same for the 4-wide node variant
 #endif
@@ -443,12 +449,13 @@ __device__ __forceinline__ void bulkLoadTop(uint4 *dst, const uint4 *src, uint32
 }
 
 template <int TOP> struct TravShape {
-  static constexpr int threads = TOP ? VR_TRAV_THREADS_TOP : 128;
+  static constexpr int threads = TOP ? VR_TRAV_THREADS_TOP : VR_TRAV_THREADS;
 };
 template <int GEO, int WIDE, int COUNT, int TOP>
-__global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : 128,
+__global__ void __launch_bounds__(TOP ? VR_TRAV_THREADS_TOP : VR_TRAV_THREADS,
                                   TOP ? VR_TRAV_BLOCKS_TOP
-                                      : (WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOCKS))
+                                      : (WIDE ? VR_TRAV_BLOCKS_WIDE : VR_TRAV_BLOCKS) * 128 /
+                                            VR_TRAV_THREADS)
     traverseKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const unsigned lane = threadIdx.x & 31u;
@@ -1182,7 +1189,9 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, cons
 }
 
 template <int D, int GEO, int EXT, int Q>
-__global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) shadeKernel(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(VR_SHADE_THREADS, (Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) * 256 /
+                                                        VR_SHADE_THREADS)
+    shadeKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t numSlots = *p.slotCount;
@@ -1299,7 +1308,8 @@ __global__ void __launch_bounds__(256, Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) 
   // independently.  Replica word 0 carries the live count of the in-place mode.
   const unsigned lane = threadIdx.x & 31u;
   unsigned long long *cnt =
-      p.counters + (size_t)((blockIdx.x * 8u + (threadIdx.x >> 5)) % VR_COUNTER_COPIES) * 8;
+      p.counters + (size_t)((blockIdx.x * (VR_SHADE_THREADS / 32u) + (threadIdx.x >> 5)) %
+                            VR_COUNTER_COPIES) * 8;
   // TraceInfo words: 1 traces, 2 misses, 3 geometry hits, 4 particle (scatter) hits,
   // 5 boundary hits, 6 reflections, 7 terminated
   const unsigned vals[8] = {stillLive ? 1u : 0u, c.cTraces, c.cMiss, c.cGeo, c.cBnd, c.cRefl,
@@ -1487,23 +1497,23 @@ cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int com
 template <int EXT> static void launchShadeExt(const TraceParams &p, unsigned grid, cudaStream_t s) {
   if (p.scene.geoType == 0) {
     if (p.scene.D == 2)
-      shadeKernel<2, 0, EXT, 0><<<grid, 256, 0, s>>>(p);
+      shadeKernel<2, 0, EXT, 0><<<grid, VR_SHADE_THREADS, 0, s>>>(p);
     else if (!EXT && p.spreadQ)  // neighbour spread queued for spreadKernel
-      shadeKernel<3, 0, 0, 1><<<grid, 256, 0, s>>>(p);
+      shadeKernel<3, 0, 0, 1><<<grid, VR_SHADE_THREADS, 0, s>>>(p);
     else
-      shadeKernel<3, 0, EXT, 0><<<grid, 256, 0, s>>>(p);
+      shadeKernel<3, 0, EXT, 0><<<grid, VR_SHADE_THREADS, 0, s>>>(p);
   } else {
     if (p.scene.D == 2)
-      shadeKernel<2, 1, EXT, 0><<<grid, 256, 0, s>>>(p);
+      shadeKernel<2, 1, EXT, 0><<<grid, VR_SHADE_THREADS, 0, s>>>(p);
     else
-      shadeKernel<3, 1, EXT, 0><<<grid, 256, 0, s>>>(p);
+      shadeKernel<3, 1, EXT, 0><<<grid, VR_SHADE_THREADS, 0, s>>>(p);
   }
 }
 
 cudaError_t launchShade(const TraceParams &p, cudaStream_t s) {
   if (p.numSlots == 0)
     return cudaSuccess;
-  const unsigned grid = (p.numSlots + 255u) / 256u;
+  const unsigned grid = (p.numSlots + VR_SHADE_THREADS - 1u) / VR_SHADE_THREADS;
   if (p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST) || p.matSticking)
     launchShadeExt<1>(p, grid, s);
   else
