@@ -7,10 +7,12 @@
 
 #define VR_INVALID_ID 0xffffffffu
 #define VR_TNEAR 1e-4f            // fillRayPosition default (rayUtil.hpp:218)
-// primitives per BVH leaf (<= 15): 8 disks measured best once the disk test lost its
-// division slow path; a triangle test costs twice a disk test and 4 stay best there
+// primitives per BVH leaf (<= 15): 8-10 disks measured best once the disk test lost its
+// division slow path (round 2, with the disk records bypassing the L1: 6 / 8 / 10 / 12 give
+// 284.3 / 279.7 / 278.0 / 289.2 ms on a 2 x 256e6-ray C4 trace; C5 does not care); a
+// triangle test costs twice a disk test and 4 stay best there
 #ifndef VR_LEAF_MAX
-#define VR_LEAF_MAX 8u
+#define VR_LEAF_MAX 10u
 #endif
 #ifndef VR_LEAF_MAX_TRI
 #define VR_LEAF_MAX_TRI 4u

@@ -926,6 +926,10 @@ struct Tally {
 // 256-bit load, bit 31 of the eighth word = "the CSR holds more"), so the common disk --
 // eight neighbours on a flat grid -- needs no offset lookup and no scalar index loads; four
 // disks are requested per round so the gathers overlap.  Integer sums: order-free.
+#ifndef VR_SPREAD_LD
+#define VR_SPREAD_LD 1  // 1: the neighbour disks of the spread with the traverse kernel's disk
+                        // policy (L1::no_allocate: +1.1 % on C4), 0: default policy
+#endif
 #ifndef VR_NB_ROWS
 #define VR_NB_ROWS 1  // 0: the CSR only (A/B switch)
 #endif
@@ -961,8 +965,13 @@ __device__ __forceinline__ void spreadNeighbors(const TraceParams &p, const uint
     float4 P[4], Nn[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (id[j] != VR_INVALID_ID)
+      if (id[j] != VR_INVALID_ID) {
+#if VR_SPREAD_LD
+        ldgDisk(&sc.prim[2 * id[j]], P[j], Nn[j]);
+#else
         ldg256(&sc.prim[2 * id[j]], P[j], Nn[j]);
+#endif
+      }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (id[j] != VR_INVALID_ID) {
