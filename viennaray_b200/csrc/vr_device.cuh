@@ -84,6 +84,20 @@ __device__ __forceinline__ void ldgDisk(const float4 *p, float4 &a, float4 &b) {
                  "=f"(b.w)
                : "l"(p));
 }
+// read-once records of the shade kernel (neighbour rows, the hit disk's normal)
+__device__ __forceinline__ void ldgOnce(const void *p, uint4 &a, uint4 &b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z),
+                 "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ float4 ldgOnce(const float4 *p) {
+  float4 a;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+               : "l"(p));
+  return a;
+}
 __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z),

@@ -44,8 +44,14 @@ namespace vr {
 #ifndef VR_TRAV_THREADS
 #define VR_TRAV_THREADS 128  // threads per traverse block (the resident warps per SM stay the same)
 #endif
+// threads per shade block: 512 for the default instantiation (+1.2 % on C4 over 256; 1024:
+// -2 %), 256 for the one that queues every hit for spreadKernel (scenes beyond the L2: C5
+// loses 0.8 % with 512)
 #ifndef VR_SHADE_THREADS
-#define VR_SHADE_THREADS 256  // threads per shade block
+#define VR_SHADE_THREADS 512
+#endif
+#ifndef VR_SHADE_THREADS_Q
+#define VR_SHADE_THREADS_Q 256
 #endif
 #ifndef VR_TRAV_BLOCKS_WIDE
 #define VR_TRAV_BLOCKS_WIDE 10  // the same for the 4-wide node variant
@@ -926,6 +932,12 @@ struct Tally {
 // 256-bit load, bit 31 of the eighth word = "the CSR holds more"), so the common disk --
 // eight neighbours on a flat grid -- needs no offset lookup and no scalar index loads; four
 // disks are requested per round so the gathers overlap.  Integer sums: order-free.
+#ifndef VR_ROW_LD
+#define VR_ROW_LD 0  // 1: neighbour rows with L1::no_allocate
+#endif
+#ifndef VR_N4_LD
+#define VR_N4_LD 0  // 1: the hit primitive's normal with L1::no_allocate
+#endif
 #ifndef VR_SPREAD_LD
 #define VR_SPREAD_LD 1  // 1: the neighbour disks of the spread with the traverse kernel's disk
                         // policy (L1::no_allocate: +1.1 % on C4), 0: default policy
@@ -942,7 +954,11 @@ __device__ __forceinline__ void spreadNeighbors(const TraceParams &p, const uint
   uint32_t k = 0u, k1 = 0u;
 #if VR_NB_ROWS
   uint4 ra, rb;
+#if VR_ROW_LD
+  ldgOnce(sc.nbRow + 2 * (size_t)hprim, ra, rb);
+#else
   ldg256(sc.nbRow + 2 * (size_t)hprim, ra, rb);
+#endif
   const bool more = rb.w != VR_INVALID_ID && (rb.w >> 31) != 0u;
   if (more)
     rb.w &= 0x7fffffffu;
@@ -1067,7 +1083,11 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, cons
     }
   } else {
     const V3 hitPoint = {org.x + dir.x * ht, org.y + dir.y * ht, org.z + dir.z * ht};
+#if VR_N4_LD
+    const float4 N4 = ldgOnce(&sc.prim[GEO == 0 ? 2 * hprim + 1 : 4 * hprim + 3]);
+#else
     const float4 N4 = __ldg(&sc.prim[GEO == 0 ? 2 * hprim + 1 : 4 * hprim + 3]);
+#endif
     const V3 gn = {N4.x, N4.y, N4.z};
     const bool backface = dot(rayDirection, gn) > 0.f;  // :224
     if (backface) {
@@ -1198,8 +1218,9 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, cons
 }
 
 template <int D, int GEO, int EXT, int Q>
-__global__ void __launch_bounds__(VR_SHADE_THREADS, (Q ? VR_SHADE_BLOCKS_Q : VR_SHADE_BLOCKS) * 256 /
-                                                        VR_SHADE_THREADS)
+__global__ void __launch_bounds__(Q ? VR_SHADE_THREADS_Q : VR_SHADE_THREADS,
+                                  Q ? VR_SHADE_BLOCKS_Q * 256 / VR_SHADE_THREADS_Q
+                                    : VR_SHADE_BLOCKS * 256 / VR_SHADE_THREADS)
     shadeKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1317,7 +1338,7 @@ __global__ void __launch_bounds__(VR_SHADE_THREADS, (Q ? VR_SHADE_BLOCKS_Q : VR_
   // independently.  Replica word 0 carries the live count of the in-place mode.
   const unsigned lane = threadIdx.x & 31u;
   unsigned long long *cnt =
-      p.counters + (size_t)((blockIdx.x * (VR_SHADE_THREADS / 32u) + (threadIdx.x >> 5)) %
+      p.counters + (size_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) %
                             VR_COUNTER_COPIES) * 8;
   // TraceInfo words: 1 traces, 2 misses, 3 geometry hits, 4 particle (scatter) hits,
   // 5 boundary hits, 6 reflections, 7 terminated
@@ -1503,12 +1524,14 @@ cudaError_t launchFlip(unsigned int *ctrl, unsigned long long *counters, int com
   return cudaGetLastError();
 }
 
-template <int EXT> static void launchShadeExt(const TraceParams &p, unsigned grid, cudaStream_t s) {
+template <int EXT> static void launchShadeExt(const TraceParams &p, cudaStream_t s) {
+  const unsigned grid = (p.numSlots + VR_SHADE_THREADS - 1u) / VR_SHADE_THREADS;
+  const unsigned gridQ = (p.numSlots + VR_SHADE_THREADS_Q - 1u) / VR_SHADE_THREADS_Q;
   if (p.scene.geoType == 0) {
     if (p.scene.D == 2)
       shadeKernel<2, 0, EXT, 0><<<grid, VR_SHADE_THREADS, 0, s>>>(p);
     else if (!EXT && p.spreadQ)  // neighbour spread queued for spreadKernel
-      shadeKernel<3, 0, 0, 1><<<grid, VR_SHADE_THREADS, 0, s>>>(p);
+      shadeKernel<3, 0, 0, 1><<<gridQ, VR_SHADE_THREADS_Q, 0, s>>>(p);
     else
       shadeKernel<3, 0, EXT, 0><<<grid, VR_SHADE_THREADS, 0, s>>>(p);
   } else {
@@ -1522,11 +1545,10 @@ template <int EXT> static void launchShadeExt(const TraceParams &p, unsigned gri
 cudaError_t launchShade(const TraceParams &p, cudaStream_t s) {
   if (p.numSlots == 0)
     return cudaSuccess;
-  const unsigned grid = (p.numSlots + VR_SHADE_THREADS - 1u) / VR_SHADE_THREADS;
   if (p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST) || p.matSticking)
-    launchShadeExt<1>(p, grid, s);
+    launchShadeExt<1>(p, s);
   else
-    launchShadeExt<0>(p, grid, s);
+    launchShadeExt<0>(p, s);
   return cudaGetLastError();
 }
 
