@@ -1,10 +1,11 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r3j_pytest.txt 2>&1; tail -3 gpurun_out/r3j_pytest.txt
-( for rep in 1 2; do for e in "X=1" "VR_POOL_SLOTS=33554432" "VR_POOL_SLOTS=50331648"; do
-  echo "C4 1e9 [$e]: $(env $e python scripts/profile_step.py 1e9 both 2>&1 | tail -1 | cut -d' ' -f6-)"
+( for rep in 1 2; do for v in k0 k_phil k_bnd; do
+  echo "$v: $(VR_LIB_PATH=$PWD/variants/$v.so python scripts/profile_step.py 256e6 both 2>&1 | tail -1 | cut -d' ' -f6-)"
+done
+for e in "VR_TAIL_RAYS=131072" "VR_TAIL_RAYS=524288" "VR_TAIL_RAYS=1048576"; do
+  echo "k0 [$e] 256e6: $(env $e VR_LIB_PATH=$PWD/variants/k0.so python scripts/profile_step.py 256e6 both 2>&1 | tail -1 | cut -d' ' -f6-)"
+  echo "k0 [$e] 125e6: $(env $e VR_LIB_PATH=$PWD/variants/k0.so python scripts/profile_step.py 125e6 both 2>&1 | tail -1 | cut -d' ' -f6-)"
 done; done
-for e in "X=1" "VR_POOL_SLOTS=33554432"; do echo "C5 [$e]: $(env $e python scripts/profile_c5.py 4e8 2>&1 | grep 'rep 1')"; done
-echo "C4 125e6 [X=1]: $(python scripts/profile_step.py 125e6 both 2>&1 | tail -1 | cut -d' ' -f6-)"
-echo "C4 125e6 [VR_POOL_SLOTS=33554432]: $(VR_POOL_SLOTS=33554432 python scripts/profile_step.py 125e6 both 2>&1 | tail -1 | cut -d' ' -f6-)" ) > gpurun_out/r3j_pool.txt 2>&1
-cat gpurun_out/r3j_pool.txt
+echo "k0 125e6: $(VR_LIB_PATH=$PWD/variants/k0.so python scripts/profile_step.py 125e6 both 2>&1 | tail -1 | cut -d' ' -f6-)" ) > gpurun_out/r3k_micro.txt 2>&1
+cat gpurun_out/r3k_micro.txt

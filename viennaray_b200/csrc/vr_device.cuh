@@ -129,7 +129,15 @@ __device__ __forceinline__ void philox4x32(uint32_t k0, uint32_t k1, uint32_t c0
 // one block of the stream, as a real call (values in registers both ways): the
 // generator is used at a dozen call sites of the shade kernel and ten inlined
 // Philox rounds per site bloat it beyond the instruction cache
-__device__ __noinline__ uint4 philoxBlock(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+#ifndef VR_PHILOX_INLINE
+#define VR_PHILOX_INLINE 0
+#endif
+#if VR_PHILOX_INLINE
+__device__ __forceinline__ uint4 philoxBlock(
+#else
+__device__ __noinline__ uint4 philoxBlock(
+#endif
+    uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
                                           uint32_t blk) {
   uint32_t o[4];
   philox4x32(k0, k1, c0, c1, blk, 0u, o);

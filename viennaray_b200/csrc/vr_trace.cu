@@ -168,7 +168,15 @@ __device__ __noinline__ Hit boundaryTestGeneric(const DeviceScene &sc, const V3 
 // expressions, same margin m), a hit with four times that margin; a ray inside a margin (corners, edges, the diagonal, a start on or
 // behind a plane) takes boundaryTestGeneric.  Same results, about a fifth of the
 // instructions (the boundary tests were 38 % of the shade kernel's).
+// the shortcut inlined at its call sites (+0.75 % on C4; the generic path stays a call)
+#ifndef VR_BOUNDARY_INLINE
+#define VR_BOUNDARY_INLINE 1
+#endif
+#if VR_BOUNDARY_INLINE
+__device__ __forceinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, const V3 dir) {
+#else
 __device__ __noinline__ Hit boundaryTest(const DeviceScene &sc, const V3 org, const V3 dir) {
+#endif
   if (!sc.bFast)
     return boundaryTestGeneric(sc, org, dir);
   const float INF = __int_as_float(0x7f800000);
