@@ -103,6 +103,22 @@ def test_call_order_and_argument_errors():
     with pytest.raises(capi.VrError) as e:  # shard outside the job
         ctx.trace(src, [part], host.config(10, SEED, 5, 20))
     assert e.value.code == 2
+    # post-processing: before any trace, then with arguments that do not go together
+    with pytest.raises(capi.VrError) as e:
+        ctx.flux_postprocess_ex()
+    assert e.value.code == 3
+    ctx.trace(src, [part], host.config(1000, SEED))
+    areas = np.ones(len(st["xyzr"]), np.float32)
+    with pytest.raises(capi.VrError) as e:  # normalisation without areas
+        ctx.flux_postprocess_ex(0, None, capi.NORM_MAX, 1.0)
+    assert e.value.code == 2
+    with pytest.raises(capi.VrError) as e:  # wider smoothing without the radius
+        ctx.flux_postprocess_ex(0, areas, capi.NORM_SOURCE, 1.0, 2, 0.0)
+    assert e.value.code == 2
+    with pytest.raises(capi.VrError) as e:  # particle index out of range
+        ctx.flux_postprocess_ex(3, areas, capi.NORM_SOURCE, 1.0)
+    assert e.value.code == 2
+    assert ctx.flux_postprocess_ex(0, areas, capi.NORM_SOURCE, 1.0, 3, 0.5).shape == (len(areas),)
     bad = st["nb"][1].copy()
     bad[0] = 10**6
     with pytest.raises(capi.VrError) as e:  # neighbour index out of range
