@@ -940,6 +940,13 @@ struct Tally {
 // 256-bit load, bit 31 of the eighth word = "the CSR holds more"), so the common disk --
 // eight neighbours on a flat grid -- needs no offset lookup and no scalar index loads; four
 // disks are requested per round so the gathers overlap.  Integer sums: order-free.
+// North-star sketch: flux adds aggregated before the global atomics.  Built as an option and
+// measured (profiles/r2_experiments.txt): the lanes of a warp almost never hit the same disk
+// (16.7M rays in flight over 1M disks, no spatial order), so the match costs more than the
+// merged atomics save.
+#ifndef VR_FLUX_AGGREGATE
+#define VR_FLUX_AGGREGATE 0
+#endif
 #ifndef VR_ROW_LD
 #define VR_ROW_LD 0  // 1: neighbour rows with L1::no_allocate
 #endif
@@ -1146,7 +1153,18 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, cons
         p.spreadQ[2 * (size_t)q + 1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(hprim));
       } else {
         const unsigned long long wf = toFixed(w);
+#if VR_FLUX_AGGREGATE
+        {  // warp-aggregated: the lanes that hit the same disk add once (integer sums)
+          const unsigned peers = __match_any_sync(__activemask(), hprim);
+          unsigned long long sum = 0ull;
+          for (unsigned m = peers; m; m &= m - 1u)
+            sum += __shfl_sync(peers, wf, __ffs(m) - 1);
+          if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1))
+            atomicAdd(&p.flux[hprim], sum);
+        }
+#else
         atomicAdd(&p.flux[hprim], wf);  // :297-306 surfaceCollision
+#endif
         ++wFlux;
         if (GEO == 0)  // :271-280 neighbour spread
           spreadNeighbors(p, hprim, org, dir, wf, wNb, wFlux);
