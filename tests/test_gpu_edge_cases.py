@@ -21,9 +21,9 @@ def tiny_case(n):
                 bc=[0, 1, 2], source_dir=host.POS_Z, kind=0, sticking=0.4, power=1.0, cone=0.0)
 
 
-@pytest.mark.parametrize("n", [1, 2, 4, 5, 8, 9, 17])
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 8, 10, 11, 17])
 def test_tiny_scenes(n):
-    """n <= 8 (VR_LEAF_MAX): the whole BVH is one leaf reference; n = 9: the first inner node."""
+    """n <= 10 (VR_LEAF_MAX): the whole BVH is one leaf reference; n = 11: the first inner node."""
     c = tiny_case(n)
     orc = common.make_oracle(c)
     ctx, src, _ = common.make_gpu(c)
