@@ -1391,7 +1391,14 @@ __global__ void __launch_bounds__(Q ? VR_SHADE_THREADS_Q : VR_SHADE_THREADS,
 // Neighbour spread as its own pass (rayTraceKernel.hpp:255-306): one thread per queued
 // geometry hit, all lanes busy, the same tests and the same fixed-point adds as the inline
 // version (integer sums: the order of the adds does not matter).
-__global__ void __launch_bounds__(256) spreadKernel(const __grid_constant__ TraceParams p) {
+#ifndef VR_SPREAD_BLOCKS
+#define VR_SPREAD_BLOCKS 3  // resident blocks per SM asked of ptxas (80 registers)
+#endif
+#ifndef VR_SPREAD_GRID
+#define VR_SPREAD_GRID 8  // blocks per SM of the grid-stride launch
+#endif
+__global__ void __launch_bounds__(256, VR_SPREAD_BLOCKS)
+    spreadKernel(const __grid_constant__ TraceParams p) {
   const DeviceScene &sc = p.scene;
   const unsigned n = *p.spreadCount;
   unsigned wNb = 0, wFlux = 0;
@@ -1419,7 +1426,7 @@ cudaError_t launchSpread(const TraceParams &p, int numSMs, cudaStream_t s) {
       p.particle.meanFreePath > 0.f || (p.flags & VR_FLAG_WDIST) || p.matSticking)
     return cudaSuccess;
   unsigned grid = (p.numSlots + 255u) / 256u;
-  const unsigned cap = (unsigned)numSMs * 8u;
+  const unsigned cap = (unsigned)numSMs * VR_SPREAD_GRID;
   if (grid > cap)
     grid = cap;
   spreadKernel<<<grid, 256, 0, s>>>(p);
