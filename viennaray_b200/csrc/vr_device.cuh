@@ -59,8 +59,15 @@ __device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
 #ifndef VR_DISK_LD
 #define VR_DISK_LD 1  // 0: default policy, 1: disks with L1::no_allocate (+0.7 % on C4: the disk records of a leaf are read once per traversal and would push node lines out), 2: L1::evict_first
 #endif
+#ifndef VR_PF_L2
+#define VR_PF_L2 0  // 1: the prefetch variants target the L2 instead of the L1
+#endif
 __device__ __forceinline__ void prefetchL1(const void *p) {
+#if VR_PF_L2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
 }
 __device__ __forceinline__ void ldgNode(const void *p, uint4 &a, uint4 &b) {
 #if VR_NODE_LD == 1
