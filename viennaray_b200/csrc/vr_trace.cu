@@ -947,6 +947,9 @@ struct Tally {
 #ifndef VR_FLUX_AGGREGATE
 #define VR_FLUX_AGGREGATE 0
 #endif
+#ifndef VR_PF_ROW
+#define VR_PF_ROW 0  // shade kernel: the neighbour row prefetched into L1, 1: beside the normal's load, 2: at the kernel's top
+#endif
 #ifndef VR_ROW_LD
 #define VR_ROW_LD 0  // 1: neighbour rows with L1::no_allocate
 #endif
@@ -1098,6 +1101,10 @@ __device__ __forceinline__ bool shadeHit(const TraceParams &p, RayState &r, cons
     }
   } else {
     const V3 hitPoint = {org.x + dir.x * ht, org.y + dir.y * ht, org.z + dir.z * ht};
+#if VR_PF_ROW == 1
+    if (GEO == 0 && !Q)
+      prefetchL1(sc.nbRow + 2 * (size_t)hprim);  // the neighbour row travels during the back-face test
+#endif
 #if VR_N4_LD
     const float4 N4 = ldgOnce(&sc.prim[GEO == 0 ? 2 * hprim + 1 : 4 * hprim + 3]);
 #else
@@ -1290,6 +1297,13 @@ __global__ void __launch_bounds__(Q ? VR_SHADE_THREADS_Q : VR_SHADE_THREADS,
       rayDirection = dir;
     }
     const float4 hv = __ldcs(&p.pool.hit[s]);
+#if VR_PF_ROW == 2
+    if (GEO == 0 && !Q && __float_as_uint(hv.z) == 1u) {
+      // the hit disk's record and its neighbour row are requested as soon as the hit is known
+      prefetchL1(&sc.prim[2 * (size_t)__float_as_uint(hv.y)]);
+      prefetchL1(sc.nbRow + 2 * (size_t)__float_as_uint(hv.y));
+    }
+#endif
     const uint4 meta = __ldcs(&p.pool.meta[s]);
     idx = (uint64_t)meta.x | ((uint64_t)meta.y << 32);
     numReflections = meta.z;
